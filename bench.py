@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the fused explicit time step on the synthetic dam-break.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+
+One "step" = one complete time step of the do-while loop of IntegrateTo
+(TimeStepper.f90:151-275): 4 fused RHS+stage kernels, the stage-1 update, maxima tracking and
+dt control.  Workload (BASELINE.json configs[4]): periodic S x S dam-break on
+xySinSlope topography, Chezy drag, erosion off, every tile active; S = 16384 on one B200 (each
+fp64 field is 2.1 GB, far beyond the 126 MB L2, so no L2 flush is needed between steps).
+
+Prints ONE JSON line.  value = whole-job cell-updates/s with the state resident in HBM, timed
+with CUDA events on the library's stream.  e2e = the same metric through the C-ABI with HOST
+buffers: kgpu_upload_domain (pinned host -> device) + K steps + kgpu_download_domain inside the
+timed region -- one output interval of the reference's Run loop (TimeStepper.f90:99-111).
+roofline = algorithmic bytes of the fused stage kernel (104 B/cell/launch) over its mean launch
+duration measured live with CUDA events.  cpu_baseline = the CPU oracle (a port; the Fortran
+reference cannot be built here) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_CELL_STAGE = 104   # read q(4)+q0(4)+b0(1), write q(4) fp64
+ALG_BYTES_PER_CELL_UPDATE = 416  # 4 stages
+CPU_SAMPLE_SIZE = 1024
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int = 0):
+        self.samples, self.reasons, self.proc = [], set(), None
+        self.index = index
+        self.max_mhz = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def oracle_library():
+    from kestrel_b200 import capi
+    path = os.path.join(ROOT, "oracle", "libkestrel_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return capi.Library(path, "kor_")
+
+
+def cpu_baseline(steps: int, warmup: int, size: int = CPU_SAMPLE_SIZE):
+    """The oracle on the host cores, bounded sample of the same workload."""
+    from kestrel_b200 import capi
+    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
+    lib = oracle_library()
+    cores = os.cpu_count() or 1
+    rs = dambreak_runset(size // 128, 128)
+    q4, b0v = dambreak_state(rs)
+    p, keep = rs.to_c()
+    st = capi.Stepper(lib, p, keep)
+    lib.set_threads(st.h, cores)
+    st.upload_domain(q4, b0v)
+    st.integrate_to(1e30, warmup)
+    t0 = time.perf_counter()
+    st.integrate_to(1e30, steps)
+    dt = time.perf_counter() - t0
+    st.close()
+    cells = rs.NX * rs.NY
+    return {"value": cells * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"{size}x{size} cells of the same dam-break, {warmup} warm-up + {steps} timed steps, OpenMP over rows "
+                      f"({cores} threads); the Fortran reference is serial and cannot be built in this image",
+            "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    cb = cpu_baseline(steps, warm)
+    line = {"impl": "reference", "metric": "cell-updates/s (fp64)", "value": cb["value"], "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off (BASELINE.json configs[4])",
+                       "cells": CPU_SAMPLE_SIZE ** 2, "note": "bounded sample of the 16384^2 workload; the reference's memory model "
+                                                               "(7 KB/cell) cannot hold the full size"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--size", type=int, default=0, help="cells per side per GPU (multiple of 128); default 16384")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    from kestrel_b200 import capi
+    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load_gpu()
+
+    size = args.size or 16384
+    free_b, total_b = torch.cuda.mem_get_info()
+    need = 30 * (size + 64) ** 2 * 8
+    while need > 0.9 * free_b and size > 1024:
+        size //= 2
+        need = 30 * (size + 64) ** 2 * 8
+    rs = dambreak_runset(size // 128, 128)
+    rs.device = local_rank
+    cells = rs.NX * rs.NY
+    q4_np, b0v_np = dambreak_state(rs)
+    # pinned host buffers (the Fortran host's arrays stand-in) for the e2e leg
+    q4 = torch.from_numpy(q4_np).pin_memory()
+    b0v = torch.from_numpy(b0v_np).pin_memory()
+    del q4_np, b0v_np
+    out = torch.empty_like(q4).pin_memory()
+
+    p, keep = rs.to_c()
+    st = capi.Stepper(lib, p, keep)
+    st.upload_domain(q4.numpy(), b0v.numpy())
+    stream = torch.cuda.ExternalStream(lib.stream(st.h))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    st.integrate_to(1e30, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.launch_count(st.h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    info = st.integrate_to(1e30, args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = int(lib.launch_count(st.h) - l0)
+    nref = int(info.nrefines)
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = cells * world * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel: mean launch duration with CUDA events on the launching stream
+    lib.rhs_timing(st.h, None, None, 1)
+    st.integrate_to(1e30, 5)
+    rms = capi.C.c_double()
+    rl = capi.C.c_int64()
+    lib.rhs_timing(st.h, capi.C.byref(rms), capi.C.byref(rl), 2)
+    k_ms = rms.value / max(rl.value, 1)
+    peak, peak_src = load_peaks()
+    achieved = cells * ALG_BYTES_PER_CELL_STAGE / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            traffic = json.load(fh).get(str(size))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "hydro_stage_kernel", "kernel_ms": k_ms, "kernel_launches_timed": int(rl.value),
+                "kernel_share_of_step": 4 * k_ms / (ms / args.steps), "peak_source": peak_src,
+                "step_frac_of_hbm_roofline": cells * ALG_BYTES_PER_CELL_UPDATE / (ms / args.steps * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = args.steps
+        barrier()
+        t0 = time.perf_counter()
+        st.upload_domain(q4.numpy(), b0v.numpy())
+        st.integrate_to(1e30, k_e2e)
+        st.lib.download_domain(st.h, capi._ptr(out.numpy()), None)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t1], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t1 = float(tt.item())
+        h2d = (q4.numel() + b0v.numel()) * 8
+        d2h = out.numel() * 8
+        e2e = {"value": cells * world * k_e2e / t1, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / k_e2e,
+               "d2h_bytes_per_step": d2h / k_e2e, "interval_steps": k_e2e, "interval_s": t1,
+               "note": "one output interval: kgpu_upload_domain + kgpu_integrate_to(K steps) + kgpu_download_domain, pinned host buffers"}
+    st.close()
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_baseline(steps=6, warmup=1)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/s (fp64)", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off, all tiles active "
+                                       "(BASELINE.json configs[4])",
+                           "cells_per_gpu": cells, "grid": f"{rs.NX}x{rs.NY}", "tiles": f"{rs.nXtiles}x{rs.nYtiles} of 128x128",
+                           "arithmetic": "faithful fp64 (no FMA contraction)", "l2": "fields are 2.1 GB each >> 126 MB L2; no flush needed",
+                           "rolled_back_attempts": nref},
+                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,842 @@
+// kestrel_gpu.cu -- host side of libkestrel_gpu: the C-ABI of include/kestrel_gpu.h.
+//
+// Replaces the body of IntegrateTo (TimeStepper.f90:116-277).  Field data never leaves
+// the device between kgpu_upload_* and kgpu_download_*; dt selection, the refine test of
+// every Runge-Kutta stage and the rollback flag live in a device-resident control block,
+// so one step costs one host synchronisation.  q0 is never overwritten inside a step:
+// a rolled-back attempt restarts from the retained stage-1 RHS (three state buffers are
+// rotated by pointer instead of the reference's five deep-copied tile containers,
+// TimeStepper.f90:785-875).
+//
+// There is no CPU execution path in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kgpu_hydro.cuh"
+#include "kgpu_morpho.cuh"
+#include "kgpu_tiles.cuh"
+
+using namespace kgpu;
+
+#define CUDA_TRY(h, call)                                                                         \
+   do {                                                                                           \
+      cudaError_t e_ = (call);                                                                    \
+      if (e_ != cudaSuccess) {                                                                    \
+         (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+         return KGPU_ERR_CUDA;                                                                    \
+      }                                                                                           \
+   } while (0)
+
+namespace {
+constexpr int BX2 = 32, BY2 = 8;   // 2-D stage tile (256 threads)
+constexpr int BX1 = 128, BY1 = 1;  // 1-D stage tile
+const double HUGE_D = std::numeric_limits<double>::max();
+}  // namespace
+
+struct kgpu_handle {
+   kgpu_params P;
+   DevParams D;
+   std::vector<DevSource> src;
+   std::string err;
+   int dev = 0;
+   cudaStream_t stream = nullptr;
+
+   int NX = 0, NY = 0, nX = 0, nY = 0, nXt = 0, nYt = 0, nTiles = 0, pitch = 0, rows = 0;
+   bool oneD = false, periodic = false, morpho = false;
+   size_t fieldElems = 0;
+
+   // device fields
+   double *S[3][4] = {};       // three rotating primary states
+   int i0 = 0, ia = 1, ib = 2; // indices of q0 / stage buffer A / stage buffer B
+   double *E0[4] = {}, *I0 = nullptr;
+   double *b0v = nullptr;
+   double *btv[4] = {};        // morphodynamics: bed change at vertices for q0 and the three stages
+   int bt0 = 0;
+   double *EBt = nullptr, *EmD = nullptr;
+   double *mx[11] = {};
+   bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
+
+   uint8_t *d_tileMask = nullptr, *d_tileSource = nullptr;
+   int2 *d_blockList = nullptr;
+   int nBlocks = 0;
+   Ctrl *d_ctrl = nullptr, *h_ctrl = nullptr;
+   DevSource *d_sources = nullptr;
+   double *d_stage = nullptr, *h_stage = nullptr;
+   size_t stageElems = 0;
+   int *d_tileList = nullptr, *d_flags = nullptr, *h_flags = nullptr;
+   RedistEntry *d_redist = nullptr, *h_redist = nullptr;
+   int redistCap = 0;
+
+   // host tile bookkeeping (UpdateTiles.f90)
+   std::vector<int> tstate;  // 0 untouched, 1 ghost, 2 active
+   std::vector<char> hasSource, loaded;
+   std::vector<int> activeList, ghostList;  // 1-based ids
+   std::vector<int> seedFlags;
+   bool firstScan = true, masksDirty = true;
+
+   double t = 0.0, dtgrid = 1.0e-5;
+   int64_t nsteps = 0, nrefines = 0, ntilesAdded = 0, launches = 0;
+   // RHS kernel timing
+   cudaEvent_t evA = nullptr, evB = nullptr;
+   bool timeRhs = false;
+   double rhsMs = 0.0;
+   int64_t rhsLaunches = 0;
+
+   bool allActive() const { return (int)activeList.size() == nTiles; }
+   StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
+   MaximaPtrs mp() const {
+      MaximaPtrs m;
+      m.Hnmax = mx[0]; m.HnmaxT = mx[1]; m.umax = mx[2]; m.umaxT = mx[3]; m.emax = mx[4]; m.emaxT = mx[5];
+      m.dmax = mx[6]; m.dmaxT = mx[7]; m.psimax = mx[8]; m.psimaxT = mx[9]; m.tfirst = mx[10];
+      return m;
+   }
+};
+
+// =========================================================================== small kernels
+__global__ void fill_kernel(double *p, size_t n, double v) {
+   size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < n) p[k] = v;
+}
+__global__ void ctrl_begin_kernel(Ctrl *c, double t) {
+   c->t = t;
+   c->cflBits[0] = 0x7FEFFFFFFFFFFFFFull;
+}
+__global__ void ctrl_set_dt_kernel(Ctrl *c, double dt) {
+   c->dt = dt;
+   c->failed = 0;
+   c->cflBits[1] = c->cflBits[2] = c->cflBits[3] = 0x7FEFFFFFFFFFFFFFull;
+}
+
+// =========================================================================== helpers
+static int roundUp(int a, int b) { return (a + b - 1) / b * b; }
+
+static void tileXY(const kgpu_handle *h, int t0, int &tx, int &ty) { tx = t0 % h->nXt; ty = t0 / h->nXt; }
+static int tileW(const kgpu_handle *h, int t0) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   if (tx == 0) return h->periodic ? (h->nXt - 1) + ty * h->nXt : -1;
+   return t0 - 1;
+}
+static int tileE(const kgpu_handle *h, int t0) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   if (tx == h->nXt - 1) return h->periodic ? ty * h->nXt : -1;
+   return t0 + 1;
+}
+static int tileS(const kgpu_handle *h, int t0) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   if (ty == 0) return h->periodic ? tx + (h->nYt - 1) * h->nXt : -1;
+   return t0 - h->nXt;
+}
+static int tileN(const kgpu_handle *h, int t0) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   if (ty == h->nYt - 1) return h->periodic ? tx : -1;
+   return t0 + h->nXt;
+}
+// Grid.f90:322-335
+static bool onDomainEdge(const kgpu_handle *h, int t0) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   bool on = (tx == 0 || tx == h->nXt - 1);
+   return on || (h->nYt > 1 && (ty == 0 || ty == h->nYt - 1));
+}
+
+static int syncStream(kgpu_handle *h) {
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return 0;
+}
+
+// Rebuild the device tile masks (with their ring) and the list of CUDA blocks that
+// overlap at least one active tile.  Only runs when the active set changed.
+static int refreshMasks(kgpu_handle *h) {
+   if (!h->masksDirty) return 0;
+   int mw = h->nXt + 2, mh = h->nYt + 2;
+   std::vector<uint8_t> mask((size_t)mw * mh, 0), srcm((size_t)mw * mh, 0);
+   for (int ty = -1; ty <= h->nYt; ty++)
+      for (int tx = -1; tx <= h->nXt; tx++) {
+         int sx = tx, sy = ty;
+         if (h->periodic) { sx = (tx + h->nXt) % h->nXt; sy = (ty + h->nYt) % h->nYt; }
+         if (sx < 0 || sx >= h->nXt || sy < 0 || sy >= h->nYt) continue;
+         int t0 = sy * h->nXt + sx;
+         mask[(size_t)(ty + 1) * mw + tx + 1] = (uint8_t)h->tstate[t0];
+         srcm[(size_t)(ty + 1) * mw + tx + 1] = (uint8_t)h->hasSource[t0];
+      }
+   CUDA_TRY(h, cudaMemcpyAsync(h->d_tileMask, mask.data(), mask.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(h->d_tileSource, srcm.data(), srcm.size(), cudaMemcpyHostToDevice, h->stream));
+   int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
+   int nbx = (h->NX + BX - 1) / BX, nby = (h->NY + BY - 1) / BY;
+   std::vector<int2> list;
+   list.reserve((size_t)nbx * nby);
+   for (int by = 0; by < nby; by++)
+      for (int bx = 0; bx < nbx; bx++) {
+         int tx0 = (bx * BX) / h->nX, tx1 = std::min(bx * BX + BX - 1, h->NX - 1) / h->nX;
+         int ty0 = (by * BY) / h->nY, ty1 = std::min(by * BY + BY - 1, h->NY - 1) / h->nY;
+         bool any = false;
+         for (int ty = ty0; ty <= ty1 && !any; ty++)
+            for (int tx = tx0; tx <= tx1; tx++)
+               if (h->tstate[ty * h->nXt + tx] == 2) { any = true; break; }
+         if (any) list.push_back(make_int2(bx, by));
+      }
+   h->nBlocks = (int)list.size();
+   if (h->nBlocks) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockList, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   h->masksDirty = false;
+   return 0;
+}
+
+// periodic wrap of the halo (single device).  Non-periodic domains need nothing: the
+// cells around the active region are static ghost data.
+static int fillHaloCells(kgpu_handle *h, int k) {
+   if (!h->periodic) return 0;
+   HaloArgs a; a.nf = 4;
+   for (int d = 0; d < 4; d++) a.f[d] = h->S[k][d];
+   if (!h->oneD) {
+      halo_periodic_x_kernel<<<(h->NY + 127) / 128, 128, 0, h->stream>>>(h->D, a, 0);
+      halo_periodic_y_kernel<<<(h->NX + 4 + 127) / 128, 128, 0, h->stream>>>(h->D, a, 0);
+      h->launches += 2;
+   } else {
+      halo_periodic_x_kernel<<<1, 32, 0, h->stream>>>(h->D, a, 0);
+      h->launches += 1;
+   }
+   return 0;
+}
+static int fillHaloVertices(kgpu_handle *h, double *v) {
+   if (!h->periodic) return 0;
+   HaloArgs a; a.nf = 1; a.f[0] = v;
+   if (!h->oneD) {
+      halo_periodic_x_kernel<<<(h->NY + 1 + 127) / 128, 128, 0, h->stream>>>(h->D, a, 1);
+      halo_periodic_y_kernel<<<(h->NX + 5 + 127) / 128, 128, 0, h->stream>>>(h->D, a, 1);
+      h->launches += 2;
+   } else {
+      halo_periodic_x_kernel<<<1, 32, 0, h->stream>>>(h->D, a, 1);
+      h->launches += 1;
+   }
+   return 0;
+}
+
+template <bool ONED>
+static void launchStageT(kgpu_handle *h, const StageArgs &a) {
+   constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
+   using G = StageGeom<BX, BY, ONED>;
+   if (h->morpho) {
+      size_t sm = G::smemBytes(true);
+      hydro_stage_kernel<BX, BY, ONED, true><<<h->nBlocks, BX * BY, sm, h->stream>>>(h->D, a);
+   } else {
+      size_t sm = G::smemBytes(false);
+      hydro_stage_kernel<BX, BY, ONED, false><<<h->nBlocks, BX * BY, sm, h->stream>>>(h->D, a);
+   }
+}
+
+// One fused RHS(+stage update) launch.  mode: StageMode; qin / qout = state buffer indices
+// (MODE_RHS writes E0/I0 instead of a state).
+static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kbt) {
+   if (h->nBlocks == 0) return 0;
+   StageArgs a;
+   for (int d = 0; d < 4; d++) {
+      a.qin[d] = h->S[kin][d];
+      a.q0[d] = h->S[h->i0][d];
+      a.qout[d] = (mode == MODE_RHS) ? h->E0[d] : h->S[kout][d];
+   }
+   a.Iout = h->I0;
+   a.b0v = h->b0v;
+   a.btv = h->morpho ? h->btv[kbt] : nullptr;
+   a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
+   a.ctrl = h->d_ctrl; a.sources = h->d_sources;
+   a.mode = mode;
+   a.allActive = h->allActive() ? 1 : 0;
+   if (h->timeRhs) cudaEventRecord(h->evA, h->stream);
+   if (h->oneD) launchStageT<true>(h, a); else launchStageT<false>(h, a);
+   if (h->timeRhs) {
+      cudaEventRecord(h->evB, h->stream);
+      cudaEventSynchronize(h->evB);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->evA, h->evB);
+      h->rhsMs += ms;
+      h->rhsLaunches++;
+   }
+   h->launches++;
+   CUDA_TRY(h, cudaGetLastError());
+   return 0;
+}
+
+static int readCtrl(kgpu_handle *h) {
+   CUDA_TRY(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return 0;
+}
+
+// =========================================================================== topography + tiles
+static int defaultTile(kgpu_handle *h, int t0, int kind) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   dim3 grid((h->nX + 127) / 128, h->nY);
+   const kgpu_params &P = h->P;
+   tile_default_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->sp(h->i0), h->sp(h->ia), h->sp(h->ib), h->b0v,
+                                                    h->morpho ? h->btv[h->bt0] : nullptr, tx, ty, kind, P.bcsHnval, P.bcsuval,
+                                                    P.bcsvval, P.bcspsival);
+   h->launches++;
+   CUDA_TRY(h, cudaGetLastError());
+   return 0;
+}
+static int ghostData(kgpu_handle *h, int t0) {
+   bool dirichlet = (h->P.bcs == KGPU_BC_DIRICHLET) && onDomainEdge(h, t0);
+   return defaultTile(h, t0, dirichlet ? 1 : 0);
+}
+
+// GetHeights + EqualiseTopographicBoundaryData (dem.f90:360, MorphodynamicRHS.f90:588-687): a
+// shared vertex takes the value of the tile for which it is local index 1.
+static int loadHeights(kgpu_handle *h, int t0, const double *given) {
+   if (h->loaded[t0] && !given) return 0;
+   int nX = h->nX, nY = h->nY;
+   size_t nv = (size_t)(nX + 1) * (nY + 1);
+   double *hb = h->h_stage;
+   if (given) {
+      std::memcpy(hb, given, sizeof(double) * (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1));
+   } else {
+      if (!h->P.heights) { h->err = "no heights callback registered and no b0_vertices given"; return KGPU_ERR_ARG; }
+      if (h->P.heights(h->P.heights_ctx, t0 + 1, hb) != 0) { h->err = "heights callback failed"; return KGPU_ERR_ARG; }
+   }
+   int tE = tileE(h, t0), tN = h->oneD ? -1 : tileN(h, t0);
+   int tNE = (tE >= 0 && !h->oneD) ? tileN(h, tE) : -1;
+   bool eL = tE >= 0 && tE != t0 && h->loaded[tE], nL = tN >= 0 && tN != t0 && h->loaded[tN], neL = tNE >= 0 && h->loaded[tNE];
+   int mask = 0;
+   if (!eL && !(h->periodic && h->nXt == 1)) mask |= 1;
+   if (!nL && !(h->periodic && h->nYt == 1)) mask |= 2;
+   if (!(eL || nL || neL) && (mask & 1) && (mask & 2)) mask |= 4;
+   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, hb, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+   int tx, ty; tileXY(h, t0, tx, ty);
+   dim3 grid((nX + 1 + 127) / 128, h->oneD ? 1 : nY + 1);
+   tile_vertices_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->b0v, h->d_stage, tx, ty, 1, mask);
+   h->launches++;
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage is reused
+   int rc = fillHaloVertices(h, h->b0v);
+   if (rc) return rc;
+   h->loaded[t0] = 1;
+   // ghost tiles sharing the refreshed seam keep w = b0 at the cell centre
+   int tW = tileW(h, t0), tS = h->oneD ? -1 : tileS(h, t0);
+   int tSW = (tW >= 0 && !h->oneD) ? tileS(h, tW) : -1;
+   for (int tt : {tW, tS, tSW})
+      if (tt >= 0 && tt != t0 && h->loaded[tt] && h->tstate[tt] == 1) {
+         rc = ghostData(h, tt);
+         if (rc) return rc;
+      }
+   return 0;
+}
+
+// UpdateTiles.f90:389-481
+static int addGhostTiles(kgpu_handle *h, int t0) {
+   int nb[8], n = 0;
+   nb[n++] = tileW(h, t0); nb[n++] = tileE(h, t0);
+   if (!h->oneD) {
+      nb[n++] = tileN(h, t0); nb[n++] = tileS(h, t0);
+      if (!h->periodic) {
+         int s = tileS(h, t0), nn = tileN(h, t0);
+         nb[n++] = s >= 0 ? tileW(h, s) : -1; nb[n++] = s >= 0 ? tileE(h, s) : -1;
+         nb[n++] = nn >= 0 ? tileW(h, nn) : -1; nb[n++] = nn >= 0 ? tileE(h, nn) : -1;
+      }
+   }
+   for (int k = 0; k < n; k++) {
+      int tt = nb[k];
+      if (tt < 0) { h->err = "ghost tile out of bounds (UpdateTiles.f90:423)"; return KGPU_ERR_ARG; }
+      if (h->tstate[tt] != 0) continue;
+      h->tstate[tt] = 1;
+      h->ghostList.push_back(tt + 1);
+      int rc = loadHeights(h, tt, nullptr);
+      if (rc) return rc;
+      rc = ghostData(h, tt);
+      if (rc) return rc;
+   }
+   return 0;
+}
+
+// AddTile (UpdateTiles.f90:56-78): AddToActiveTiles + AllocateTile + ActivateTile
+static int addTile(kgpu_handle *h, int t0, bool countIt) {
+   if (t0 < 0 || t0 >= h->nTiles || (onDomainEdge(h, t0) && !h->periodic)) {
+      if (h->P.bcs == KGPU_BC_HALT) {
+         h->err = "tried to add a tile outside the domain (Boundary Conditions = halt)";
+         return KGPU_ERR_HALT_BC;
+      }
+      return 0;
+   }
+   if (h->tstate[t0] == 2) return 0;
+   bool wasGhost = h->tstate[t0] == 1;
+   h->tstate[t0] = 2;
+   h->activeList.insert(std::upper_bound(h->activeList.begin(), h->activeList.end(), t0 + 1), t0 + 1);
+   if (wasGhost) h->ghostList.erase(std::find(h->ghostList.begin(), h->ghostList.end(), t0 + 1));
+   h->hasSource[t0] = 0;
+   h->masksDirty = true;
+   int rc = loadHeights(h, t0, nullptr);
+   if (rc) return rc;
+   rc = defaultTile(h, t0, wasGhost ? 2 : 0);  // fresh tile: zeros + w = b0; promoted ghost: w = b0
+   if (rc) return rc;
+   rc = addGhostTiles(h, t0);
+   if (countIt) h->ntilesAdded++;
+   return rc;
+}
+
+// CheckIfNearBoundaries (TimeStepper.f90:924-1150): flags on the device, list replay on the host
+static int checkIfNearBoundaries(kgpu_handle *h) {
+   if (h->allActive()) { h->firstScan = false; return 0; }
+   int nAct = (int)h->activeList.size();
+   if (nAct == 0) return 0;
+   std::vector<int> flags(h->nTiles, 0);
+   if (h->firstScan) {
+      for (int id : h->activeList) flags[id - 1] = h->seedFlags[id - 1];
+   } else {
+      std::vector<int> tl(nAct);
+      for (int k = 0; k < nAct; k++) tl[k] = h->activeList[k] - 1;
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_tileList, tl.data(), nAct * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      tile_flags_kernel<<<nAct, 128, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, h->morpho ? h->btv[h->bt0] : nullptr,
+                                                     h->d_tileList, h->P.TileBuffer, h->d_flags);
+      h->launches++;
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_flags, h->d_flags, nAct * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      for (int k = 0; k < nAct; k++) flags[tl[k]] = h->h_flags[k];
+   }
+   int buf = h->P.TileBuffer;
+   // replay of the four passes with the trip count fixed at loop entry (quirk Q3)
+   for (int dir = (h->oneD ? 2 : 0); dir < 4; dir++) {
+      int trip = (int)h->activeList.size();
+      for (int tt = 0; tt < trip; tt++) {
+         int t0 = h->activeList[tt] - 1;
+         int tx, ty; tileXY(h, t0, tx, ty);
+         int nbr;
+         switch (dir) {
+            case 0: nbr = (h->periodic && ty == h->nYt - 1) ? tx : t0 + h->nXt; break;
+            case 1: nbr = (h->periodic && ty == 0) ? tx + (h->nYt - 1) * h->nXt : t0 - h->nXt; break;
+            case 2: nbr = (h->periodic && tx == h->nXt - 1) ? ty * h->nXt : t0 + 1; break;
+            default: nbr = (h->periodic && tx == 0) ? (h->nXt - 1) + ty * h->nXt : t0 - 1; break;
+         }
+         if (nbr + 1 <= 0) continue;
+         if (nbr < h->nTiles && h->tstate[nbr] == 2) continue;
+         int f = flags[t0];
+         bool trig;
+         switch (dir) {
+            case 0: trig = (f & 1) || (0 > h->nY - buf); break;
+            case 1: trig = (f & 2) || (h->nY <= buf); break;
+            case 2: trig = (f & 4) || (0 > h->nX - buf); break;
+            default: trig = (f & 8) || (h->nX <= buf); break;
+         }
+         if (trig) {
+            int rc = addTile(h, nbr, true);
+            if (rc) return rc;
+         }
+      }
+   }
+   h->firstScan = false;
+   return 0;
+}
+
+// TimeStepper.f90:281-305
+static double nextFluxSeriesTime(const kgpu_handle *h, double t) {
+   double nextT = HUGE_D, tdiff = HUGE_D;
+   for (const DevSource &S : h->src)
+      for (int j = 0; j < S.n; j++) {
+         double tmp = S.time[j] - t;
+         if (tmp > 0.0 && tmp < tdiff) { tdiff = tmp; nextT = S.time[j]; }
+      }
+   return nextT;
+}
+
+// =========================================================================== the step
+// substep-1 RHS of state kin -> E0, I0 and the advised dt (HydraulicRHS.f90:64-174)
+static int firstRHS(kgpu_handle *h, int kin, int kbt, double tNow, double tmax, int setDt) {
+   int rc = fillHaloCells(h, kin);
+   if (rc) return rc;
+   ctrl_begin_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, tNow);
+   rc = launchStage(h, MODE_RHS, kin, -1, kbt);
+   if (rc) return rc;
+   ctrl_advise_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, h->allActive() ? 0 : 1, tmax, setDt);
+   h->launches += 2;
+   return 0;
+}
+
+// HydraulicTimeStepper (TimeStepper.f90:333-527) with dt taken from the control block.
+// On return h_ctrl is current; h_ctrl->failed != 0 means "refine" with dtNew.
+static int hydraulicTimeStepper(kgpu_handle *h, int kbt) {
+   int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
+   int some = h->allActive() ? 0 : 1;
+   // stage 1 (elementwise; E0/I0 retained for cheap retries)
+   Update1Args u;
+   for (int d = 0; d < 4; d++) { u.q0[d] = h->S[h->i0][d]; u.E[d] = h->E0[d]; u.q1[d] = h->S[h->ia][d]; }
+   u.I = h->I0; u.tileMask = h->d_tileMask; u.blockList = h->d_blockList; u.ctrl = h->d_ctrl; u.allActive = h->allActive() ? 1 : 0;
+   if (h->nBlocks) {
+      if (h->oneD) stage1_update_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, u);
+      else stage1_update_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, u);
+      h->launches++;
+   }
+   int rc;
+   if ((rc = fillHaloCells(h, h->ia))) return rc;
+   if ((rc = launchStage(h, MODE_STAGE2, h->ia, h->ib, kbt))) return rc;
+   ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 1);
+   if ((rc = fillHaloCells(h, h->ib))) return rc;
+   if ((rc = launchStage(h, MODE_STAGE3, h->ib, h->ia, kbt))) return rc;
+   ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 2);
+   if ((rc = fillHaloCells(h, h->ia))) return rc;
+   if ((rc = launchStage(h, MODE_FINAL, h->ia, h->ib, kbt))) return rc;
+   h->launches += 2;
+   // maxima on the step-start state, stamped t + dt (quirk Q1)
+   if (h->nBlocks) {
+      if (h->oneD)
+         maxima_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, h->morpho ? h->btv[kbt] : nullptr,
+                                                                       h->mp(), h->d_tileMask, h->d_blockList, h->d_ctrl, u.allActive);
+      else
+         maxima_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, h->morpho ? h->btv[kbt] : nullptr,
+                                                                       h->mp(), h->d_tileMask, h->d_blockList, h->d_ctrl, u.allActive);
+      h->launches++;
+   }
+   CUDA_TRY(h, cudaGetLastError());
+   return readCtrl(h);
+}
+
+#include "kgpu_morpho_host.inl"
+
+static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_info *info) {
+   int64_t done = 0;
+   double dt_hydro = h->dtgrid;
+   bool integrating = tend > h->t;
+   int rc;
+   while (integrating) {
+      if ((rc = checkIfNearBoundaries(h))) return rc;
+      if ((rc = refreshMasks(h))) return rc;
+      double t0 = h->t;
+      double tmax = std::min(tend, nextFluxSeriesTime(h, h->t));
+      if ((rc = firstRHS(h, h->i0, h->bt0, h->t, tmax, h->morpho ? 2 : 1))) return rc;
+      int guard = 0;
+      while (true) {
+         if (++guard > 200) { h->err = "time step underflow (200 refinements of one step)"; return KGPU_ERR_DT; }
+         if ((rc = hydraulicTimeStepper(h, h->bt0))) return rc;
+         if (h->h_ctrl->nonfinite) { h->err = "non-finite state"; return KGPU_ERR_DT; }
+         dt_hydro = h->h_ctrl->dt;
+         if (!(dt_hydro > 0.0) || !std::isfinite(dt_hydro)) { h->err = "time step underflow"; return KGPU_ERR_DT; }
+         if (h->h_ctrl->failed) {
+            h->nrefines++;
+            dt_hydro = h->h_ctrl->dtNew;
+            ctrl_set_dt_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, dt_hydro);
+            h->launches++;
+            continue;
+         }
+         if (!h->morpho) break;
+         bool again = false;
+         if ((rc = strangRemainder(h, t0, dt_hydro, again))) return rc;
+         if (!again) break;
+      }
+      // CopySolutionData(intermed3 -> tileContainer) by pointer rotation
+      std::swap(h->i0, h->ib);
+      h->havePre = true;
+      h->t = h->morpho ? t0 + 2.0 * dt_hydro : t0 + dt_hydro;
+      h->dtgrid = dt_hydro;
+      h->nsteps++;
+      done++;
+      if (h->t >= tend) integrating = false;
+      if (maxSteps > 0 && done >= maxSteps) integrating = false;
+   }
+   if (info) {
+      info->t = h->t; info->dt_last = dt_hydro; info->nsteps = h->nsteps; info->nrefines = h->nrefines; info->ntiles_added = h->ntilesAdded;
+   }
+   return 0;
+}
+
+// =========================================================================== C-ABI
+extern "C" {
+
+const char *kgpu_version(void) { return "kestrel-b200 0.1 (sm_100a)"; }
+const char *kgpu_last_error(const kgpu_handle *h) { return h ? h->err.c_str() : "null handle"; }
+int64_t kgpu_launch_count(const kgpu_handle *h) { return h ? h->launches : 0; }
+void *kgpu_stream(kgpu_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int kgpu_rhs_timing(kgpu_handle *h, double *ms, int64_t *launches, int32_t reset) {
+   if (!h) return KGPU_ERR_ARG;
+   if (ms) *ms = h->rhsMs;
+   if (launches) *launches = h->rhsLaunches;
+   if (reset == 1) { h->rhsMs = 0.0; h->rhsLaunches = 0; h->timeRhs = true; }
+   if (reset == 2) { h->timeRhs = false; }
+   return 0;
+}
+
+int kgpu_destroy(kgpu_handle *h) {
+   if (!h) return 0;
+   cudaSetDevice(h->dev);
+   if (h->stream) cudaStreamSynchronize(h->stream);
+   for (int k = 0; k < 3; k++) for (int d = 0; d < 4; d++) cudaFree(h->S[k][d]);
+   for (int d = 0; d < 4; d++) { cudaFree(h->E0[d]); cudaFree(h->btv[d]); }
+   cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
+   for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
+   cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
+   cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist);
+   cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
+   if (h->evA) cudaEventDestroy(h->evA);
+   if (h->evB) cudaEventDestroy(h->evB);
+   if (h->stream) cudaStreamDestroy(h->stream);
+   delete h;
+   return 0;
+}
+
+int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
+   if (!p || !out || p->struct_bytes != (int32_t)sizeof(kgpu_params)) return KGPU_ERR_ARG;
+   if (p->n_sources > MAX_SOURCES) return KGPU_ERR_UNSUPPORTED;
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KGPU_ERR_CUDA;  // no CPU fallback
+   kgpu_handle *h = new kgpu_handle();
+   h->P = *p;
+   h->P.sources = nullptr;
+   if (p->device >= 0) { h->dev = p->device; if (cudaSetDevice(h->dev) != cudaSuccess) { delete h; return KGPU_ERR_CUDA; } }
+   else cudaGetDevice(&h->dev);
+   for (int s = 0; s < p->n_sources; s++) {
+      const kgpu_source &k = p->sources[s];
+      if (k.n_series > MAX_SERIES || k.n_series < 1) { delete h; return KGPU_ERR_UNSUPPORTED; }
+      DevSource S;
+      std::memset(&S, 0, sizeof(S));
+      S.x = k.x; S.y = k.y; S.radius = k.radius; S.numCells = k.num_cells_in_src; S.n = k.n_series;
+      for (int j = 0; j < k.n_series; j++) { S.time[j] = k.time[j]; S.flux[j] = k.flux[j]; S.psi[j] = k.psi[j]; }
+      h->src.push_back(S);
+   }
+   h->nX = p->nXpertile; h->nY = p->nYpertile; h->nXt = p->nXtiles; h->nYt = p->nYtiles;
+   h->NX = h->nX * h->nXt; h->NY = h->nY * h->nYt; h->nTiles = h->nXt * h->nYt;
+   h->oneD = p->isOneD != 0; h->periodic = p->bcs == KGPU_BC_PERIODIC; h->morpho = p->MorphodynamicsOn != 0;
+   int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
+   h->pitch = roundUp(XO + roundUp(h->NX, BX) + 8, 16);
+   h->rows = h->oneD ? (YO + 1 + 3) : (YO + roundUp(h->NY, BY) + 4);
+   h->fieldElems = (size_t)h->pitch * h->rows;
+
+   DevParams &D = h->D;
+   std::memset(&D, 0, sizeof(D));
+   D.NX = h->NX; D.NY = h->NY; D.nX = h->nX; D.nY = h->nY; D.nXt = h->nXt; D.nYt = h->nYt;
+   D.gtx0 = 0; D.gty0 = 0; D.gnXt = h->nXt; D.gnYt = h->nYt;
+   D.pitch = h->pitch; D.rows = h->rows;
+   D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
+   D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;
+   D.eroTrans = p->erosion_transition; D.damp = p->morpho_damp; D.fswitch = p->fswitch;
+   D.nSources = p->n_sources;
+   D.dx = p->deltaX; D.dy = p->deltaY; D.dxR = 1.0 / p->deltaX; D.dyR = 1.0 / p->deltaY; D.xSize = p->xSize; D.ySize = p->ySize;
+   D.g = p->g; D.rhow = p->rhow; D.rhos = p->rhos; D.gred = p->gred;
+   D.ChezyCo = p->ChezyCo; D.ManningCo = p->ManningCo; D.CoulombCo = p->CoulombCo;
+   D.PoulMin = p->PouliquenMinSlope; D.PoulMax = p->PouliquenMaxSlope; D.PoulInt = p->PouliquenIntermediateSlope; D.PoulBeta = p->PouliquenBeta;
+   D.EdBetastar = p->Edwards2019betastar; D.EdKappa = p->Edwards2019kappa; D.EdGamma = p->Edwards2019Gamma;
+   D.SwitchRate = p->VoellmySwitchRate; D.SwitchValue = p->VoellmySwitchValue;
+   D.EroRate = p->EroRate; D.EroRateGranular = p->EroRateGranular; D.CriticalShields = p->CriticalShields; D.EroDepth = p->EroDepth;
+   D.EroCritH = p->EroCriticalHeight; D.BedPorosity = p->BedPorosity; D.maxPack = p->maxPack; D.SolidDiameter = p->SolidDiameter;
+   D.ws0 = p->ws0; D.nsettling = p->nsettling; D.nu = p->EddyViscosity;
+   D.Hneps = p->heightThreshold; D.cfl = p->cfl; D.diffusiveTimeScale = p->diffusiveTimeScale; D.maxdt = p->maxdt;
+
+   h->tstate.assign(h->nTiles, 0); h->hasSource.assign(h->nTiles, 0); h->loaded.assign(h->nTiles, 0); h->seedFlags.assign(h->nTiles, 0);
+   h->t = p->tstart;
+
+   auto fail = [&](const char *what) { fprintf(stderr, "kgpu_create: %s: %s\n", what, cudaGetErrorString(cudaGetLastError())); kgpu_destroy(h); return KGPU_ERR_CUDA; };
+   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+   cudaEventCreate(&h->evA); cudaEventCreate(&h->evB);
+   size_t fb = h->fieldElems * sizeof(double);
+   auto allocField = [&](double **ptr, double fillv) -> bool {
+      if (cudaMalloc(ptr, fb) != cudaSuccess) return false;
+      if (fillv == 0.0) return cudaMemsetAsync(*ptr, 0, fb, h->stream) == cudaSuccess;
+      fill_kernel<<<(unsigned)((h->fieldElems + 255) / 256), 256, 0, h->stream>>>(*ptr, h->fieldElems, fillv);
+      return true;
+   };
+   for (int k = 0; k < 3; k++) for (int d = 0; d < 4; d++) if (!allocField(&h->S[k][d], 0.0)) return fail("state");
+   for (int d = 0; d < 4; d++) if (!allocField(&h->E0[d], 0.0)) return fail("E0");
+   if (!allocField(&h->I0, 0.0) || !allocField(&h->b0v, 0.0)) return fail("I0/b0v");
+   if (h->morpho) {
+      for (int d = 0; d < 4; d++) if (!allocField(&h->btv[d], 0.0)) return fail("btv");
+      if (!allocField(&h->EBt, 0.0) || !allocField(&h->EmD, 0.0)) return fail("EBt");
+   }
+   for (int k = 0; k < 10; k++) if (!allocField(&h->mx[k], 0.0)) return fail("maxima");
+   if (!allocField(&h->mx[10], -1.0)) return fail("tfirst");
+   size_t msz = (size_t)(h->nXt + 2) * (h->nYt + 2);
+   int nbx = (h->NX + BX - 1) / BX, nby = (h->NY + BY - 1) / BY;
+   if (cudaMalloc(&h->d_tileMask, msz) != cudaSuccess || cudaMalloc(&h->d_tileSource, msz) != cudaSuccess) return fail("masks");
+   if (cudaMalloc(&h->d_blockList, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess) return fail("blocklist");
+   if (cudaMalloc(&h->d_ctrl, sizeof(Ctrl)) != cudaSuccess || cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)) != cudaSuccess) return fail("ctrl");
+   cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream);
+   std::memset(h->h_ctrl, 0, sizeof(Ctrl));
+   if (cudaMalloc(&h->d_sources, sizeof(DevSource) * std::max<size_t>(1, h->src.size())) != cudaSuccess) return fail("sources");
+   if (!h->src.empty()) cudaMemcpyAsync(h->d_sources, h->src.data(), sizeof(DevSource) * h->src.size(), cudaMemcpyHostToDevice, h->stream);
+   size_t ncell = (size_t)h->nX * h->nY, nv = (size_t)(h->nX + 1) * (h->nY + 1);
+   h->stageElems = 24 * ncell + 2 * nv;
+   if (cudaMalloc(&h->d_stage, h->stageElems * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stageElems * sizeof(double)) != cudaSuccess) return fail("stage");
+   if (cudaMalloc(&h->d_tileList, sizeof(int) * h->nTiles) != cudaSuccess || cudaMalloc(&h->d_flags, sizeof(int) * h->nTiles) != cudaSuccess ||
+       cudaMallocHost(&h->h_flags, sizeof(int) * h->nTiles) != cudaSuccess) return fail("flags");
+   if (h->morpho) {
+      h->redistCap = 1 << 16;
+      if (cudaMalloc(&h->d_redist, sizeof(RedistEntry) * h->redistCap) != cudaSuccess ||
+          cudaMallocHost(&h->h_redist, sizeof(RedistEntry) * h->redistCap) != cudaSuccess) return fail("redist");
+   }
+   // opt in to > 48 KB dynamic shared memory for the stage kernel
+   cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX2, BY2, false>::smemBytes(false));
+   cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX2, BY2, false>::smemBytes(true));
+   cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX1, BY1, true>::smemBytes(false));
+   cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX1, BY1, true>::smemBytes(true));
+   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
+   *out = h;
+   return KGPU_OK;
+}
+
+int kgpu_upload_tile(kgpu_handle *h, int32_t tile_id, const double *u13, const double *b0_vertices, const double *bt_vertices,
+                     const double *maxima, const double *tfirst, int32_t contains_source) {
+   if (!h || !u13) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   int t0 = tile_id - 1;
+   if (t0 < 0 || t0 >= h->nTiles) { h->err = "tile id out of range"; return KGPU_ERR_ARG; }
+   int rc;
+   if (b0_vertices && (rc = loadHeights(h, t0, b0_vertices))) return rc;
+   if ((rc = addTile(h, t0, false))) return rc;
+   if (h->tstate[t0] != 2) { h->err = "tile lies on the domain edge and cannot be active"; return KGPU_ERR_ARG; }
+   h->hasSource[t0] = contains_source ? 1 : 0;
+   h->masksDirty = true;
+   int nX = h->nX, nY = h->nY;
+   size_t ncell = (size_t)nX * nY;
+   int tx, ty; tileXY(h, t0, tx, ty);
+   if (bt_vertices && h->morpho) {
+      size_t nv = (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1);
+      std::memcpy(h->h_stage, bt_vertices, nv * sizeof(double));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      dim3 gridv((nX + 1 + 127) / 128, h->oneD ? 1 : nY + 1);
+      tile_vertices_kernel<<<gridv, 128, 0, h->stream>>>(h->D, h->btv[h->bt0], h->d_stage, tx, ty, 1, 7);
+      h->launches++;
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      if ((rc = fillHaloVertices(h, h->btv[h->bt0]))) return rc;
+   }
+   std::memcpy(h->h_stage, u13, ncell * 13 * sizeof(double));
+   if (maxima) std::memcpy(h->h_stage + ncell * 13, maxima, ncell * 10 * sizeof(double));
+   if (tfirst) std::memcpy(h->h_stage + ncell * 23, tfirst, ncell * sizeof(double));
+   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, ncell * 24 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+   dim3 grid((nX + 127) / 128, nY);
+   import_tile_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->sp(h->i0), h->mp(), h->d_stage, tx, ty, maxima ? 1 : 0, tfirst ? 1 : 0);
+   h->launches++;
+   CUDA_TRY(h, cudaGetLastError());
+   // seed of the first tile-activation scan: the host's u(Hn) (TimeStepper.f90:982)
+   int buf = h->P.TileBuffer, f = 0;
+   for (int lj = 0; lj < nY; lj++)
+      for (int li = 0; li < nX; li++) {
+         if (u13[((size_t)lj * nX + li) * 13 + 4] > h->P.heightThreshold) {
+            if (!h->oneD) { if (lj >= nY - buf) f |= 1; if (lj < buf) f |= 2; }
+            if (li >= nX - buf) f |= 4;
+            if (li < buf) f |= 8;
+         }
+      }
+   h->seedFlags[t0] = f;
+   h->havePre = false;
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return KGPU_OK;
+}
+
+int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertices, const double *bt_vertices) {
+   if (!h || !q4 || !b0_vertices) return KGPU_ERR_ARG;
+   if (!h->periodic) { h->err = "kgpu_upload_domain needs Boundary Conditions = periodic (UpdateTiles.f90:61-69)"; return KGPU_ERR_ARG; }
+   cudaSetDevice(h->dev);
+   size_t nc = (size_t)h->NX * h->NY;
+   size_t dp = (size_t)h->pitch * sizeof(double);
+   for (int d = 0; d < 4; d++)
+      CUDA_TRY(h, cudaMemcpy2DAsync(h->S[h->i0][d] + (size_t)YO * h->pitch + XO, dp, q4 + d * nc, (size_t)h->NX * sizeof(double),
+                                    (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyHostToDevice, h->stream));
+   int nvy = h->oneD ? 1 : h->NY + 1;
+   CUDA_TRY(h, cudaMemcpy2DAsync(h->b0v + (size_t)YO * h->pitch + XO, dp, b0_vertices, (size_t)(h->NX + 1) * sizeof(double),
+                                 (size_t)(h->NX + 1) * sizeof(double), nvy, cudaMemcpyHostToDevice, h->stream));
+   int rc;
+   if ((rc = fillHaloVertices(h, h->b0v))) return rc;
+   if (h->morpho && bt_vertices) {
+      CUDA_TRY(h, cudaMemcpy2DAsync(h->btv[h->bt0] + (size_t)YO * h->pitch + XO, dp, bt_vertices, (size_t)(h->NX + 1) * sizeof(double),
+                                    (size_t)(h->NX + 1) * sizeof(double), nvy, cudaMemcpyHostToDevice, h->stream));
+      if ((rc = fillHaloVertices(h, h->btv[h->bt0]))) return rc;
+   }
+   h->activeList.clear(); h->ghostList.clear();
+   for (int t0 = 0; t0 < h->nTiles; t0++) { h->tstate[t0] = 2; h->loaded[t0] = 1; h->activeList.push_back(t0 + 1); }
+   h->masksDirty = true;
+   h->firstScan = false;
+   h->havePre = false;
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return KGPU_OK;
+}
+
+int kgpu_integrate_to(kgpu_handle *h, double tend, int64_t max_steps, kgpu_step_info *info) {
+   if (!h) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   return integrateTo(h, tend, max_steps, info);
+}
+
+int kgpu_active_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
+   if (!h || !n) return KGPU_ERR_ARG;
+   *n = (int32_t)h->activeList.size();
+   if (ids) for (size_t k = 0; k < h->activeList.size(); k++) ids[k] = h->activeList[k];
+   return KGPU_OK;
+}
+int kgpu_ghost_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
+   if (!h || !n) return KGPU_ERR_ARG;
+   *n = (int32_t)h->ghostList.size();
+   if (ids) for (size_t k = 0; k < h->ghostList.size(); k++) ids[k] = h->ghostList[k];
+   return KGPU_OK;
+}
+
+int kgpu_download_tile(kgpu_handle *h, int32_t tile_id, double *u13, double *b0_vertices, double *bt_vertices, double *maxima, double *tfirst) {
+   if (!h) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   int t0 = tile_id - 1;
+   if (t0 < 0 || t0 >= h->nTiles) { h->err = "tile id out of range"; return KGPU_ERR_ARG; }
+   int nX = h->nX, nY = h->nY;
+   size_t ncell = (size_t)nX * nY, nv = (size_t)(nX + 1) * (nY + 1), nvu = (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1);
+   int tx, ty; tileXY(h, t0, tx, ty);
+   dim3 grid((nX + 127) / 128, nY);
+   export_tile_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->sp(h->i0), h->sp(h->ia), h->havePre ? 1 : 0, h->b0v,
+                                                   h->morpho ? h->btv[h->bt0] : nullptr, h->mp(), h->d_stage, tx, ty);
+   dim3 gridv((nX + 1 + 127) / 128, h->oneD ? 1 : nY + 1);
+   tile_vertices_kernel<<<gridv, 128, 0, h->stream>>>(h->D, h->b0v, h->d_stage + 24 * ncell, tx, ty, 0, 0);
+   if (h->morpho) tile_vertices_kernel<<<gridv, 128, 0, h->stream>>>(h->D, h->btv[h->bt0], h->d_stage + 24 * ncell + nv, tx, ty, 0, 0);
+   else CUDA_TRY(h, cudaMemsetAsync(h->d_stage + 24 * ncell + nv, 0, nv * sizeof(double), h->stream));
+   h->launches += h->morpho ? 3 : 2;
+   CUDA_TRY(h, cudaMemcpyAsync(h->h_stage, h->d_stage, h->stageElems * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   if (u13) std::memcpy(u13, h->h_stage, ncell * 13 * sizeof(double));
+   if (maxima) std::memcpy(maxima, h->h_stage + ncell * 13, ncell * 10 * sizeof(double));
+   if (tfirst) std::memcpy(tfirst, h->h_stage + ncell * 23, ncell * sizeof(double));
+   if (b0_vertices) std::memcpy(b0_vertices, h->h_stage + 24 * ncell, nvu * sizeof(double));
+   if (bt_vertices) std::memcpy(bt_vertices, h->h_stage + 24 * ncell + nv, nvu * sizeof(double));
+   return KGPU_OK;
+}
+
+int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices) {
+   if (!h) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   size_t nc = (size_t)h->NX * h->NY;
+   size_t dp = (size_t)h->pitch * sizeof(double);
+   if (q4)
+      for (int d = 0; d < 4; d++)
+         CUDA_TRY(h, cudaMemcpy2DAsync(q4 + d * nc, (size_t)h->NX * sizeof(double), h->S[h->i0][d] + (size_t)YO * h->pitch + XO, dp,
+                                       (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyDeviceToHost, h->stream));
+   if (bt_vertices) {
+      int nvy = h->oneD ? 1 : h->NY + 1;
+      if (h->morpho)
+         CUDA_TRY(h, cudaMemcpy2DAsync(bt_vertices, (size_t)(h->NX + 1) * sizeof(double), h->btv[h->bt0] + (size_t)YO * h->pitch + XO, dp,
+                                       (size_t)(h->NX + 1) * sizeof(double), nvy, cudaMemcpyDeviceToHost, h->stream));
+      else std::memset(bt_vertices, 0, sizeof(double) * (size_t)(h->NX + 1) * nvy);
+   }
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return KGPU_OK;
+}
+
+// One evaluation of CalculateHydraulicRHS on the current state (parity probe for K1).
+int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, double *dt) {
+   if (!h) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   int rc;
+   if ((rc = refreshMasks(h))) return rc;
+   if ((rc = firstRHS(h, h->i0, h->bt0, h->t, HUGE_D, 0))) return rc;
+   if ((rc = readCtrl(h))) return rc;
+   size_t nc = (size_t)h->NX * h->NY;
+   size_t dp = (size_t)h->pitch * sizeof(double);
+   if (E4)
+      for (int d = 0; d < 4; d++)
+         CUDA_TRY(h, cudaMemcpy2DAsync(E4 + d * nc, (size_t)h->NX * sizeof(double), h->E0[d] + (size_t)YO * h->pitch + XO, dp,
+                                       (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyDeviceToHost, h->stream));
+   if (I)
+      CUDA_TRY(h, cudaMemcpy2DAsync(I, (size_t)h->NX * sizeof(double), h->I0 + (size_t)YO * h->pitch + XO, dp,
+                                    (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyDeviceToHost, h->stream));
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   if (dt) *dt = (substep == 1) ? h->h_ctrl->dtAdvised : h->h_ctrl->dtAdvised / 0.9;
+   return KGPU_OK;
+}
+
+int kgpu_comm_id_bytes(void) { return 128; }
+int kgpu_comm_create_id(void *) { return KGPU_ERR_UNSUPPORTED; }
+int kgpu_comm_attach(kgpu_handle *, const void *, int32_t, int32_t, int32_t, int32_t) { return KGPU_ERR_UNSUPPORTED; }
+
+}  // extern "C"

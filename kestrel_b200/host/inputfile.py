@@ -177,3 +177,53 @@ def read_input_file(path: str) -> RunSet:
         assert len(fs.time) == len(fs.flux) == len(fs.psi), "sourceTime/Flux/Conc sets differ in length"
         rs.sources.append(fs)
     return rs
+
+
+def write_input_file(rs: RunSet, path: str, header: str = "") -> None:
+    """Emit a RunSet in Kestrel's input format (normalised: one key per line, no comments
+    other than the header).  read_input_file(write_input_file(rs)) round-trips."""
+    def g(v):
+        return repr(float(v))
+    L = []
+    if header:
+        L += [f"% {ln}" for ln in header.splitlines()]
+    L += ["Domain:", "Lat = 0", "Lon = 0", f"nXtiles = {rs.nXtiles}", f"nYtiles = {rs.nYtiles}",
+          f"nXpertile = {rs.nXpertile}", f"nYpertile = {rs.nYpertile}", f"Xtilesize = {g(rs.Xtilesize)}",
+          f"Boundary Conditions = {rs.bcs}"]
+    if rs.bcs == "dirichlet":
+        L += [f"Boundary Hn = {g(rs.bcsHnval)}", f"Boundary u = {g(rs.bcsuval)}", f"Boundary v = {g(rs.bcsvval)}",
+              f"Boundary psi = {g(rs.bcspsival)}"]
+    for c in rs.caps:
+        L += ["", "Cap:", f"capX = {g(c.x)}", f"capY = {g(c.y)}", f"capRadius = {g(c.radius)}", f"capHeight = {g(c.height)}",
+              f"capU = {g(c.u)}", f"capV = {g(c.v)}", f"capConc = {g(c.psi)}", f"capShape = {c.shape}"]
+    for c in rs.cubes:
+        L += ["", "Cube:", f"cubeX = {g(c.x)}", f"cubeY = {g(c.y)}", f"cubeLength = {g(c.length)}", f"cubeWidth = {g(c.width)}",
+              f"cubeHeight = {g(c.height)}", f"cubeU = {g(c.u)}", f"cubeV = {g(c.v)}", f"cubeConc = {g(c.psi)}",
+              f"cubeShape = {c.shape}"]
+    for s in rs.sources:
+        st = lambda xs: "(" + ", ".join(g(x) for x in xs) + ")"
+        L += ["", "Source:", f"sourceX = {g(s.x)}", f"sourceY = {g(s.y)}", f"sourceRadius = {g(s.radius)}",
+              f"sourceTime = {st(s.time)}", f"sourceFlux = {st(s.flux)}", f"sourceConc = {st(s.psi)}"]
+    L += ["", "Parameters:", f"Drag = {rs.drag}", f"Erosion = {rs.erosion}", f"Deposition = {rs.deposition}",
+          f"Erosion Transition = {rs.erosion_transition}", f"Morphodynamic damping = {rs.morpho_damp}",
+          f"Switch function = {rs.fswitch}", f"Geometric factors = {'on' if rs.geometric_factors else 'off'}"]
+    for key, attr in [("g", "g"), ("Chezy Co", "ChezyCo"), ("Manning Co", "ManningCo"), ("Coulomb Co", "CoulombCo"),
+                      ("Pouliquen Min", "PouliquenMinSlope"), ("Pouliquen Max", "PouliquenMaxSlope"),
+                      ("Pouliquen Intermediate", "PouliquenIntermediateSlope"), ("Pouliquen beta", "PouliquenBeta"),
+                      ("Edwards2019 betastar", "Edwards2019betastar"), ("Edwards2019 kappa", "Edwards2019kappa"),
+                      ("Edwards2019 gamma", "Edwards2019Gamma"), ("Voellmy switch rate", "VoellmySwitchRate"),
+                      ("Voellmy switch value", "VoellmySwitchValue"), ("Erosion Rate", "EroRate"),
+                      ("Granular Erosion Rate", "EroRateGranular"), ("Erosion depth", "EroDepth"),
+                      ("Erosion critical height", "EroCriticalHeight"), ("Bed porosity", "BedPorosity"),
+                      ("rhow", "rhow"), ("rhos", "rhos"), ("maxPack", "maxPack"), ("Solid diameter", "SolidDiameter"),
+                      ("Eddy Viscosity", "EddyViscosity")]:
+        L.append(f"{key} = {g(getattr(rs, attr))}")
+    L += ["", "Solver:", f"T start = {g(rs.tstart)}", f"T end = {g(rs.tend)}", f"limiter = {rs.limiter}",
+          f"Height threshold = {g(rs.heightThreshold)}", f"Tile Buffer = {rs.TileBuffer}", f"cfl = {g(rs.cfl)}"]
+    if rs.maxdt < 1e300:
+        L.append(f"max dt = {g(rs.maxdt)}")
+    L += ["", "Output:", f"N out = {rs.Nout}", f"directory = {rs.out_dir}", "",
+          "Topog:", "Type = Function", f"Topog function = {rs.topog_func}",
+          "Topog params = (" + ", ".join(g(x) for x in rs.topog_params) + ")", ""]
+    with open(path, "w") as fh:
+        fh.write("\n".join(L))

@@ -121,6 +121,7 @@ struct Oracle {
    // loop bounds: bounding box of the active tiles + 2 cells (cells [ilo,ihi) x [jlo,jhi))
    int ilo = 0, ihi = 0, jlo = 0, jhi = 0;
    void updateBounds() {
+      refreshCellAct();
       if (activeList.empty()) { ilo = ihi = jlo = jhi = 0; return; }
       int a = NX, b = 0, c = NY, d = 0;
       for (int id : activeList) {
@@ -134,19 +135,37 @@ struct Oracle {
    }
 
    // ---------------------------------------------------------------- indexing
-   inline int wrapi(int i) const { return periodic ? ((i % NX) + NX) % NX : std::min(std::max(i, 0), NX - 1); }
-   inline int wrapj(int j) const { return periodic ? ((j % NY) + NY) % NY : std::min(std::max(j, 0), NY - 1); }
-   inline int cidx(int i, int j) const { return wrapj(j) * NX + wrapi(i); }
-   inline int vwi(int i) const { return periodic ? ((i % NX) + NX) % NX : std::min(std::max(i, 0), NXV - 1); }
-   inline int vwj(int j) const {
-      if (oneD) return 0;
-      return periodic ? ((j % NY) + NY) % NY : std::min(std::max(j, 0), NYV - 1);
-   }
-   inline int vidx(int i, int j) const { return vwj(j) * NXV + vwi(i); }
+   // wrap / clamp tables for i in [-4, NX+4) and the halo'd per-cell activity mask: the
+   // inner loops index these instead of dividing (the reference follows tile pointers)
+   vector<int> wxT, wyT, vxT, vyT;
+   vector<unsigned char> cellAct;  // (NX+4) x (NY+4), halo 2
+   inline int wrapi(int i) const { return wxT[i + 4]; }
+   inline int wrapj(int j) const { return wyT[j + 4]; }
+   inline int cidx(int i, int j) const { return wyT[j + 4] * NX + wxT[i + 4]; }
+   inline int vwi(int i) const { return vxT[i + 4]; }
+   inline int vwj(int j) const { return oneD ? 0 : vyT[j + 4]; }
+   inline int vidx(int i, int j) const { return (oneD ? 0 : vyT[j + 4]) * NXV + vxT[i + 4]; }
    inline int fxidx(int fi, int j) const { return j * (NX + 1) + fi; }  // x-faces (NX+1) x NY
    inline int fyidx(int i, int fj) const { return fj * NX + i; }        // y-faces NX x (NY+1)
    inline int tileOfCell(int i, int j) const { return (wrapi(i) / nX) + (wrapj(j) / nY) * nXt; }
-   inline bool cellActive(int i, int j) const { return tstate[tileOfCell(i, j)] == 2; }
+   inline bool cellActive(int i, int j) const { return cellAct[(size_t)(j + 2) * (NX + 4) + (i + 2)] != 0; }
+   void buildTables() {
+      wxT.resize(NX + 8); wyT.resize(NY + 8); vxT.resize(NX + 9); vyT.resize(NY + 9);
+      for (int i = -4; i < NX + 4; i++) wxT[i + 4] = periodic ? ((i % NX) + NX) % NX : std::min(std::max(i, 0), NX - 1);
+      for (int j = -4; j < NY + 4; j++) wyT[j + 4] = periodic ? ((j % NY) + NY) % NY : std::min(std::max(j, 0), NY - 1);
+      for (int i = -4; i < NX + 5; i++) vxT[i + 4] = periodic ? ((i % NX) + NX) % NX : std::min(std::max(i, 0), NXV - 1);
+      for (int j = -4; j < NY + 5; j++) vyT[j + 4] = periodic ? ((j % NY) + NY) % NY : std::min(std::max(j, 0), std::max(NYV - 1, 0));
+      cellAct.assign((size_t)(NX + 4) * (NY + 4), 0);
+   }
+   void refreshCellAct() {
+      for (int j = -2; j < NY + 2; j++)
+         for (int i = -2; i < NX + 2; i++) {
+            bool in = periodic || (i >= 0 && i < NX && j >= 0 && j < NY);
+            unsigned char a = 0;
+            if (in) a = tstate[(wxT[i + 4] / nX) + (wyT[j + 4] / nY) * nXt] == 2 ? 1 : 0;
+            cellAct[(size_t)(j + 2) * (NX + 4) + (i + 2)] = a;
+         }
+   }
 
    // Closures.f90:269-305
    inline double gamma2(double bx, double by) const { return geom ? std::sqrt(1.0 + bx * bx + by * by) : 1.0; }
@@ -1689,6 +1708,7 @@ struct Oracle {
       oneD = P.isOneD != 0; periodic = P.bcs == KGPU_BC_PERIODIC; geom = P.geometric_factors != 0;
       NXV = NX + 1; NYV = oneD ? 1 : NY + 1;
       dx = P.deltaX; dy = P.deltaY; dxR = 1.0 / dx; dyR = 1.0 / dy;
+      buildTables();
       tstate.assign(nTiles, 0); hasSource.assign(nTiles, 0); loaded.assign(nTiles, 0);
       size_t nc = (size_t)NX * NY, nv = (size_t)NXV * NYV;
       b0v.assign(nv, 0.0);

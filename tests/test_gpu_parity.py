@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): state fields agree to rel-Linf 1e-10 per field after
+the same step count; lake at rest exact to round-off; depth non-negative; active-tile
+set identical.  For hydraulic runs with Chezy drag every operation on the path is
++,-,*,/,sqrt -- IEEE-exact on both sides -- so the faithful variant is required to be
+BIT-IDENTICAL there; closures that call tanh/log/pow get the 1e-10 bar.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import INPUTS, compare_snapshots, domain_stepper, rel_linf, run_input
+from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10  # relative L-infinity per field (north_star)
+
+
+def _both(oracle_lib, gpu_lib, rs, q4, b0v, steps):
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io = so.integrate_to(1e9, steps)
+    ig = sg.integrate_to(1e9, steps)
+    return so, sg, io, ig
+
+
+def test_rhs_single_evaluation_bit_exact(oracle_lib, gpu_lib):
+    """One CalculateHydraulicRHS on the dam-break state: E (4 planes), I and dt."""
+    rs = dambreak_runset(2, 64)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    Eo, Io, dto = so.debug_rhs(1)
+    Eg, Ig, dtg = sg.debug_rhs(1)
+    assert dto == dtg
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert np.array_equal(Eo[d], Eg[d]), f"ddtExplicit({name}) differs, rel {rel_linf(Eg[d], Eo[d])}"
+    assert np.array_equal(Io, Ig)
+
+
+@pytest.mark.parametrize("ntiles,per", [(2, 64), (3, 50), (1, 40)])
+def test_dambreak_periodic_bit_exact(oracle_lib, gpu_lib, ntiles, per):
+    """Synthetic dam-break (the bench workload, small): ragged tile sizes included."""
+    rs = dambreak_runset(ntiles, per)
+    q4, b0v = dambreak_state(rs)
+    so, sg, io, ig = _both(oracle_lib, gpu_lib, rs, q4, b0v, 60)
+    assert (io.t, io.dt_last, io.nsteps, io.nrefines) == (ig.t, ig.dt_last, ig.nsteps, ig.nrefines)
+    qo, qg = so.download_domain(), sg.download_domain()
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert np.array_equal(qo[d], qg[d]), f"{name}: rel-Linf {rel_linf(qg[d], qo[d])}"
+
+
+def test_dambreak_viscous_limiters(oracle_lib, gpu_lib):
+    """Eddy viscosity on (diffusion fluxes + diffusive dt cap) and every limiter."""
+    for lim in ["minmod1", "minmod2", "none", "van albada", "weno"]:
+        rs = dambreak_runset(2, 32, EddyViscosity=0.05, limiter=lim)
+        q4, b0v = dambreak_state(rs)
+        so, sg, io, ig = _both(oracle_lib, gpu_lib, rs, q4, b0v, 25)
+        assert io.t == ig.t, lim
+        qo, qg = so.download_domain(), sg.download_domain()
+        for d in range(4):
+            assert np.array_equal(qo[d], qg[d]), f"limiter {lim} field {d}: {rel_linf(qg[d], qo[d])}"
+
+
+@pytest.mark.parametrize("drag", ["coulomb", "voellmy", "pouliquen", "edwards2019", "variable", "manning"])
+def test_drag_closures(oracle_lib, gpu_lib, drag):
+    """All seven runtime-selectable drags (Closures.f90:365-558); tanh/pow paths get 1e-10."""
+    rs = dambreak_runset(2, 32, drag=drag)
+    q4, b0v = dambreak_state(rs)
+    q4[3] = 0.3 * (q4[0] - 0.0) * 0.1  # some solids so the switch function matters
+    so, sg, io, ig = _both(oracle_lib, gpu_lib, rs, q4, b0v, 25)
+    qo, qg = so.download_domain(), sg.download_domain()
+    assert abs(io.t - ig.t) <= 1e-12 * abs(io.t)
+    for d in range(4):
+        assert rel_linf(qg[d], qo[d]) <= TOL, f"{drag} field {d}"
+
+
+def test_geometric_factors_off(oracle_lib, gpu_lib):
+    rs = dambreak_runset(2, 32, geometric_factors=False)
+    q4, b0v = dambreak_state(rs)
+    so, sg, io, ig = _both(oracle_lib, gpu_lib, rs, q4, b0v, 25)
+    qo, qg = so.download_domain(), sg.download_domain()
+    for d in range(4):
+        assert np.array_equal(qo[d], qg[d])
+
+
+def test_lake_at_rest_2d(oracle_lib, gpu_lib):
+    """tests/Input_lake_at_rest_hydro_2d.txt: depth must not move at the 10 printed digits the
+    reference's check_no_flow compares (testlib.jl:332-358) and GPU == oracle bit for bit."""
+    path = os.path.join(INPUTS, "case_lake_at_rest_hydro_2d.txt")
+    sg = run_input(gpu_lib, path)
+    so = run_input(oracle_lib, path)
+    Hn0 = sg.snapshots[0][1]["u"][..., 4]
+    for snap in sg.snapshots[1:]:
+        Hn = snap[1]["u"][..., 4]
+        assert np.all(np.char.mod("%.10E", Hn) == np.char.mod("%.10E", Hn0))
+        assert np.max(np.abs(Hn - Hn0)) < 1e-14
+    res = compare_snapshots(sg.snapshots[-1], so.snapshots[-1])
+    for name, (err, exact) in res.items():
+        assert exact, f"{name}: {err}"
+
+
+def test_1d_cap_example_bit_exact(oracle_lib, gpu_lib):
+    """examples/Input1d_cap_constslope.txt (BASELINE configs[0]): 1-D, halt BC, dynamic tiles."""
+    path = os.path.join(INPUTS, "case_1d_cap_constslope.txt")
+    sg = run_input(gpu_lib, path, tend=30.0, Nout=2)
+    so = run_input(oracle_lib, path, tend=30.0, Nout=2)
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert (sg.infos[-1].nsteps, sg.infos[-1].nrefines) == (so.infos[-1].nsteps, so.infos[-1].nrefines)
+    res = compare_snapshots(sg.snapshots[-1], so.snapshots[-1])
+    for name, (err, exact) in res.items():
+        assert exact, f"{name}: {err}"
+    Hn = np.concatenate([t["u"][..., 4].ravel() for t in sg.snapshots[-1].values()])
+    assert Hn.min() >= -1e-14
+
+
+def test_2d_flux_source_dynamic_tiles(oracle_lib, gpu_lib):
+    """tests/Input_flux_hydro_2d.txt shortened: flux source, halt BC, tile activation; active set
+    must match bit-exactly and the delivered volume must be conserved to 1e-10."""
+    path = os.path.join(INPUTS, "case_flux_hydro_2d.txt")
+    sg = run_input(gpu_lib, path, tend=4.0, Nout=2, nXpertile=10, nYpertile=10, nXtiles=60, nYtiles=60, Xtilesize=10.0)
+    so = run_input(oracle_lib, path, tend=4.0, Nout=2, nXpertile=10, nYpertile=10, nXtiles=60, nYtiles=60, Xtilesize=10.0)
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert len(sg.stepper.active_tiles()) > len(sg.ic_tiles)
+    res = compare_snapshots(sg.snapshots[-1], so.snapshots[-1])
+    for name, (err, exact) in res.items():
+        assert exact, f"{name}: {err}"
+    v0, vn = sg.volume_rows[0], sg.volume_rows[-1]
+    delivered = 10.0 * 1.0  # sourceFlux 10 over [0, 1]
+    assert abs((vn[1] + vn[2]) - (v0[1] + v0[2]) - delivered) / delivered < 1e-10
+    # maxima + first-inundation times are part of the download contract
+    for k in sg.snapshots[-1]:
+        assert np.array_equal(sg.snapshots[-1][k]["maxima"], so.snapshots[-1][k]["maxima"])
+        assert np.array_equal(sg.snapshots[-1][k]["tfirst"], so.snapshots[-1][k]["tfirst"])
+
+
+def test_halt_boundary_error_code(gpu_lib):
+    """Flow reaching the domain edge with bcs = halt is reported as KGPU_ERR_HALT_BC (UpdateTiles.f90:63-65)."""
+    from kestrel_b200 import capi
+    path = os.path.join(INPUTS, "case_1d_cap_constslope.txt")
+    with pytest.raises(capi.KestrelError) as ei:
+        run_input(gpu_lib, path, nXtiles=4, tend=200.0, Nout=1)
+    assert ei.value.code == capi.KGPU_ERR_HALT_BC
+
+
+def test_full_size_properties(gpu_lib):
+    """Size-independent properties at a large grid (2048^2, 4.2 M cells): volume conservation to
+    1e-10, non-negative depth, x-mirror symmetry of the setup is not assumed."""
+    rs = dambreak_runset(16, 128)
+    q4, b0v = dambreak_state(rs)
+    from kestrel_b200.host.sources import centre_topography, gamma
+    b0c, _, bx, by = centre_topography(rs, b0v)
+    g2 = gamma(rs, bx, by) ** 2
+    vol0 = float(np.sum((q4[0] - b0c) * g2))
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    info = sg.integrate_to(1e9, 40)
+    q = sg.download_domain()
+    vol1 = float(np.sum((q[0] - b0c) * g2))
+    assert info.nsteps == 40
+    assert abs(vol1 - vol0) / vol0 < 1e-10
+    assert np.min(q[0] - b0c) >= -1e-14
