@@ -51,12 +51,16 @@ struct kgpu_handle {
    size_t fieldElems = 0;
 
    // device fields
-   double *S[3][4] = {};       // three rotating primary states
+   double *S[5][4] = {};       // rotating primary states: 3 (hydraulic) or 5 (Strang split)
+   int nStates = 3;
    int i0 = 0, ia = 1, ib = 2; // indices of q0 / stage buffer A / stage buffer B
+   int ic = 3, id = 4;         // morphodynamics: state after M, second H result
+   bool e0Valid = false;       // E0/I0 hold the substep-1 RHS of S[i0]
+   double *Um = nullptr, *Vm = nullptr;  // velocities frozen over M
    double *E0[4] = {}, *I0 = nullptr;
    double *b0v = nullptr;
    double *btv[4] = {};        // morphodynamics: bed change at vertices for q0 and the three stages
-   int bt0 = 0;
+   int bt0 = 0, bt1 = 1, bt2 = 2, bt3 = 3;
    double *EBt = nullptr, *EmD = nullptr;
    double *mx[11] = {};
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
@@ -231,12 +235,12 @@ static void launchStageT(kgpu_handle *h, const StageArgs &a) {
 
 // One fused RHS(+stage update) launch.  mode: StageMode; qin / qout = state buffer indices
 // (MODE_RHS writes E0/I0 instead of a state).
-static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kbt) {
+static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int kbt) {
    if (h->nBlocks == 0) return 0;
    StageArgs a;
    for (int d = 0; d < 4; d++) {
       a.qin[d] = h->S[kin][d];
-      a.q0[d] = h->S[h->i0][d];
+      a.q0[d] = h->S[kq0][d];
       a.qout[d] = (mode == MODE_RHS) ? h->E0[d] : h->S[kout][d];
    }
    a.Iout = h->I0;
@@ -272,9 +276,12 @@ static int defaultTile(kgpu_handle *h, int t0, int kind) {
    int tx, ty; tileXY(h, t0, tx, ty);
    dim3 grid((h->nX + 127) / 128, h->nY);
    const kgpu_params &P = h->P;
-   tile_default_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->sp(h->i0), h->sp(h->ia), h->sp(h->ib), h->b0v,
-                                                    h->morpho ? h->btv[h->bt0] : nullptr, tx, ty, kind, P.bcsHnval, P.bcsuval,
-                                                    P.bcsvval, P.bcspsival);
+   AllStates all;
+   all.n = h->nStates;
+   const int order[5] = {h->i0, h->ia, h->ib, h->ic, h->id};
+   for (int k = 0; k < h->nStates; k++) for (int d = 0; d < 4; d++) all.q[k][d] = h->S[order[k]][d];
+   tile_default_kernel<<<grid, 128, 0, h->stream>>>(h->D, all, h->b0v, h->morpho ? h->btv[h->bt0] : nullptr, tx, ty, kind,
+                                                    P.bcsHnval, P.bcsuval, P.bcsvval, P.bcspsival);
    h->launches++;
    CUDA_TRY(h, cudaGetLastError());
    return 0;
@@ -445,7 +452,7 @@ static int firstRHS(kgpu_handle *h, int kin, int kbt, double tNow, double tmax, 
    int rc = fillHaloCells(h, kin);
    if (rc) return rc;
    ctrl_begin_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, tNow);
-   rc = launchStage(h, MODE_RHS, kin, -1, kbt);
+   rc = launchStage(h, MODE_RHS, kin, -1, kin, kbt);
    if (rc) return rc;
    ctrl_advise_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, h->allActive() ? 0 : 1, tmax, setDt);
    h->launches += 2;
@@ -454,12 +461,12 @@ static int firstRHS(kgpu_handle *h, int kin, int kbt, double tNow, double tmax, 
 
 // HydraulicTimeStepper (TimeStepper.f90:333-527) with dt taken from the control block.
 // On return h_ctrl is current; h_ctrl->failed != 0 means "refine" with dtNew.
-static int hydraulicTimeStepper(kgpu_handle *h, int kbt) {
+static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt) {
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
    int some = h->allActive() ? 0 : 1;
    // stage 1 (elementwise; E0/I0 retained for cheap retries)
    Update1Args u;
-   for (int d = 0; d < 4; d++) { u.q0[d] = h->S[h->i0][d]; u.E[d] = h->E0[d]; u.q1[d] = h->S[h->ia][d]; }
+   for (int d = 0; d < 4; d++) { u.q0[d] = h->S[kq0][d]; u.E[d] = h->E0[d]; u.q1[d] = h->S[ka][d]; }
    u.I = h->I0; u.tileMask = h->d_tileMask; u.blockList = h->d_blockList; u.ctrl = h->d_ctrl; u.allActive = h->allActive() ? 1 : 0;
    if (h->nBlocks) {
       if (h->oneD) stage1_update_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, u);
@@ -467,23 +474,24 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kbt) {
       h->launches++;
    }
    int rc;
-   if ((rc = fillHaloCells(h, h->ia))) return rc;
-   if ((rc = launchStage(h, MODE_STAGE2, h->ia, h->ib, kbt))) return rc;
+   if ((rc = fillHaloCells(h, ka))) return rc;
+   if ((rc = launchStage(h, MODE_STAGE2, ka, kb, kq0, kbt))) return rc;
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 1);
-   if ((rc = fillHaloCells(h, h->ib))) return rc;
-   if ((rc = launchStage(h, MODE_STAGE3, h->ib, h->ia, kbt))) return rc;
+   if ((rc = fillHaloCells(h, kb))) return rc;
+   if ((rc = launchStage(h, MODE_STAGE3, kb, ka, kq0, kbt))) return rc;
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 2);
-   if ((rc = fillHaloCells(h, h->ia))) return rc;
-   if ((rc = launchStage(h, MODE_FINAL, h->ia, h->ib, kbt))) return rc;
+   if ((rc = fillHaloCells(h, ka))) return rc;
+   if ((rc = launchStage(h, MODE_FINAL, ka, kb, kq0, kbt))) return rc;
    h->launches += 2;
-   // maxima on the step-start state, stamped t + dt (quirk Q1)
+   // maxima on the state at the start of the whole step (tileContainer), stamped t + dt (quirk Q1)
    if (h->nBlocks) {
+      const double *btm = h->morpho ? h->btv[h->bt0] : nullptr;
       if (h->oneD)
-         maxima_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, h->morpho ? h->btv[kbt] : nullptr,
-                                                                       h->mp(), h->d_tileMask, h->d_blockList, h->d_ctrl, u.allActive);
+         maxima_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
+                                                                       h->d_blockList, h->d_ctrl, u.allActive);
       else
-         maxima_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, h->morpho ? h->btv[kbt] : nullptr,
-                                                                       h->mp(), h->d_tileMask, h->d_blockList, h->d_ctrl, u.allActive);
+         maxima_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
+                                                                       h->d_blockList, h->d_ctrl, u.allActive);
       h->launches++;
    }
    CUDA_TRY(h, cudaGetLastError());
@@ -503,27 +511,39 @@ static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_
       double t0 = h->t;
       double tmax = std::min(tend, nextFluxSeriesTime(h, h->t));
       if ((rc = firstRHS(h, h->i0, h->bt0, h->t, tmax, h->morpho ? 2 : 1))) return rc;
-      int guard = 0;
+      h->e0Valid = true;
+      bool haveDt = false;  // false: dt comes from ctrl_advise; true: the host dictates dt_hydro
+      int guard = 0, kres = h->ib;
       while (true) {
          if (++guard > 200) { h->err = "time step underflow (200 refinements of one step)"; return KGPU_ERR_DT; }
-         if ((rc = hydraulicTimeStepper(h, h->bt0))) return rc;
+         if (!h->e0Valid) {  // E0/I0 were reused by the second H operator: re-evaluate (rare)
+            if ((rc = firstRHS(h, h->i0, h->bt0, t0, tmax, 0))) return rc;
+            h->e0Valid = true;
+         }
+         if (haveDt) {
+            ctrl_set_dt_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, dt_hydro);
+            h->launches++;
+         }
+         if ((rc = hydraulicTimeStepper(h, h->i0, h->ia, h->ib, h->bt0))) return rc;
          if (h->h_ctrl->nonfinite) { h->err = "non-finite state"; return KGPU_ERR_DT; }
          dt_hydro = h->h_ctrl->dt;
          if (!(dt_hydro > 0.0) || !std::isfinite(dt_hydro)) { h->err = "time step underflow"; return KGPU_ERR_DT; }
          if (h->h_ctrl->failed) {
             h->nrefines++;
             dt_hydro = h->h_ctrl->dtNew;
-            ctrl_set_dt_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, dt_hydro);
-            h->launches++;
+            haveDt = true;
             continue;
          }
          if (!h->morpho) break;
          bool again = false;
          if ((rc = strangRemainder(h, t0, dt_hydro, again))) return rc;
-         if (!again) break;
+         if (!again) { kres = h->id; break; }
+         haveDt = true;
       }
       // CopySolutionData(intermed3 -> tileContainer) by pointer rotation
-      std::swap(h->i0, h->ib);
+      if (!h->morpho) std::swap(h->i0, h->ib);
+      else { std::swap(h->i0, h->id); std::swap(h->bt0, h->bt3); }
+      (void)kres;
       h->havePre = true;
       h->t = h->morpho ? t0 + 2.0 * dt_hydro : t0 + dt_hydro;
       h->dtgrid = dt_hydro;
@@ -559,7 +579,8 @@ int kgpu_destroy(kgpu_handle *h) {
    if (!h) return 0;
    cudaSetDevice(h->dev);
    if (h->stream) cudaStreamSynchronize(h->stream);
-   for (int k = 0; k < 3; k++) for (int d = 0; d < 4; d++) cudaFree(h->S[k][d]);
+   for (int k = 0; k < 5; k++) for (int d = 0; d < 4; d++) cudaFree(h->S[k][d]);
+   cudaFree(h->Um); cudaFree(h->Vm);
    for (int d = 0; d < 4; d++) { cudaFree(h->E0[d]); cudaFree(h->btv[d]); }
    cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
@@ -633,12 +654,13 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       fill_kernel<<<(unsigned)((h->fieldElems + 255) / 256), 256, 0, h->stream>>>(*ptr, h->fieldElems, fillv);
       return true;
    };
-   for (int k = 0; k < 3; k++) for (int d = 0; d < 4; d++) if (!allocField(&h->S[k][d], 0.0)) return fail("state");
+   h->nStates = h->morpho ? 5 : 3;
+   for (int k = 0; k < h->nStates; k++) for (int d = 0; d < 4; d++) if (!allocField(&h->S[k][d], 0.0)) return fail("state");
    for (int d = 0; d < 4; d++) if (!allocField(&h->E0[d], 0.0)) return fail("E0");
    if (!allocField(&h->I0, 0.0) || !allocField(&h->b0v, 0.0)) return fail("I0/b0v");
    if (h->morpho) {
       for (int d = 0; d < 4; d++) if (!allocField(&h->btv[d], 0.0)) return fail("btv");
-      if (!allocField(&h->EBt, 0.0) || !allocField(&h->EmD, 0.0)) return fail("EBt");
+      if (!allocField(&h->EmD, 0.0) || !allocField(&h->Um, 0.0) || !allocField(&h->Vm, 0.0)) return fail("EmD");
    }
    for (int k = 0; k < 10; k++) if (!allocField(&h->mx[k], 0.0)) return fail("maxima");
    if (!allocField(&h->mx[10], -1.0)) return fail("tfirst");

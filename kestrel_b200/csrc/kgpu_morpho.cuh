@@ -1,10 +1,338 @@
-// kgpu_morpho.cuh -- morphodynamic operator M (MorphodynamicRHS.f90, TimeStepper.f90:532-781).
+// kgpu_morpho.cuh -- the morphodynamic operator M of the Strang split
+// (MorphodynamicRHS.f90:72-305, TimeStepper.f90:532-781, Redistribute.f90).
+//
+// Per Runge-Kutta stage: (1) E - D at cell centres, zeroed beside dry cells; (2) vertex
+// source -gamma_v/(4 psi_b) * Kahan(E-D of the 4 cells) and the bed update with the erosion
+// depth clamp; (3) the linear, conservative update of w and Hnpsi from the new bed.  The
+// velocities u, v are frozen over M at the values of the last hydraulic RHS evaluation
+// (ComputeDesingularisedVariables(computeVelocities=.false.), TimeStepper.f90:609).
 #pragma once
 #include "kgpu_device.cuh"
+#include "kgpu_tiles.cuh"
 
 namespace kgpu {
+
 struct RedistEntry {
    double excess;
    int i, j;
 };
+
+__device__ __forceinline__ int wrapIdx(int i, int n, int periodic) { return periodic ? ((i % n) + n) % n : i; }
+
+struct MorphoArgs {
+   const double *w, *hpsi;      // stage state (w, Hnpsi)
+   const double *w0, *hpsi0;    // state at the start of M (intermed0)
+   const double *U, *V;         // frozen velocities
+   const double *b0v;
+   const double *btk;           // bed of the stage state
+   const double *bt0;           // bed at the start of M
+   double *btn;                 // bed being written
+   double *wn, *hpsin;          // stage state being written
+   double *EmD;
+   const uint8_t *tileMask;
+   const int2 *blockList;
+   Ctrl *ctrl;
+   int allActive;
+   double a0, a1;               // RK weights: bt_new = a0*bt0 + a1*(btk + dt*rhs); a0 = 0 selects stage 1
+   double dtMorpho;
+};
+
+__device__ __forceinline__ bool cellTileActive(const DevParams &P, const uint8_t *mask, int allActive, int ci, int cj) {
+   if (allActive) return ci >= -2 && ci < P.NX + 2 && cj >= -2 && cj < P.NY + 2;
+   int tx = (ci >= 0 ? ci / P.nX : -1) + 1, ty = (cj >= 0 ? cj / P.nY : -1) + 1;
+   if (tx > P.nXt + 1 || ty > P.nYt + 1) return false;
+   return mask[ty * (P.nXt + 2) + tx] == 2;
+}
+
+// stored u(Hn) of a container: ComputeHn clamped at zero (HydraulicRHS.f90:808, 840-842)
+__device__ __forceinline__ double storedHn(const DevParams &P, const double *w, const double *b0v, const double *btv, int ci, int cj) {
+   double b0c, btc, bx, by;
+   centreTopoGlobal(P, b0v, btv, ci, cj, b0c, btc, bx, by);
+   double Hn = computeHn(w[(size_t)(cj + YO) * P.pitch + (ci + XO)], b0c, btc, gamma2(P, bx, by));
+   return Hn < 0.0 ? 0.0 : Hn;
+}
+
+// velocities of the hydraulic result as its 4th RHS evaluation left them (pre-correction momenta)
+template <int BX, int BY>
+__global__ void __launch_bounds__(BX *BY) morpho_prepare_kernel(const DevParams P, const double *w, const double *hpsi, const double *huPre,
+                                                                const double *hvPre, const double *b0v, const double *btv, double *U,
+                                                                double *V, const uint8_t *tileMask, const int2 *blockList, int allActive) {
+   const int2 bo = blockList[blockIdx.x];
+   int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
+   if (ci >= P.NX || cj >= P.NY) return;
+   if (!cellTileActive(P, tileMask, allActive, ci, cj)) return;
+   size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+   CellState q;
+   q.w = w[g]; q.hpsi = hpsi[g]; q.hu = huPre[g]; q.hv = hvPre[g];
+   centreTopoGlobal(P, b0v, btv, ci, cj, q.b0, q.bt, q.bx, q.by);
+   desingularise(P, q, true);
+   U[g] = q.u; V[g] = q.v;
+}
+
+// CalculateMorphodynamicRHS, cell part (MorphodynamicRHS.f90:96-145)
+template <int BX, int BY>
+__global__ void __launch_bounds__(BX *BY) morpho_emd_kernel(const DevParams P, const MorphoArgs A) {
+   const int2 bo = A.blockList[blockIdx.x];
+   int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
+   if (ci >= P.NX || cj >= P.NY) return;
+   if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) return;
+   size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+   CellState q;
+   q.w = A.w[g]; q.hpsi = A.hpsi[g]; q.hu = 0.0; q.hv = 0.0;
+   centreTopoGlobal(P, A.b0v, A.btk, ci, cj, q.b0, q.bt, q.bx, q.by);
+   desingularise(P, q, false);
+   q.u = A.U[g]; q.v = A.V[g];
+   double eps = P.Hneps;
+   bool dry = q.Hn < eps || storedHn(P, A.w, A.b0v, A.btk, ci - 1, cj) < eps || storedHn(P, A.w, A.b0v, A.btk, ci + 1, cj) < eps;
+   if (!P.oneD) dry = dry || storedHn(P, A.w, A.b0v, A.btk, ci, cj - 1) < eps || storedHn(P, A.w, A.b0v, A.btk, ci, cj + 1) < eps;
+   A.EmD[g] = dry ? 0.0 : erosionMinusDeposition(P, q);
+}
+
+// BtSourceTerm (MorphodynamicRHS.f90:154-305) + the bed stage update (TimeStepper.f90:574-581 etc.)
+__global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
+   int vi = blockIdx.x * blockDim.x + threadIdx.x;
+   int vj = blockIdx.y;
+   int nvy = P.oneD ? 1 : P.NY + 1;
+   if (vi > P.NX || vj >= nvy) return;
+   if (P.periodic && (vi == P.NX || (!P.oneD && vj == P.NY))) return;  // aliases, refreshed by the halo fill
+   // vertex of an active tile?
+   bool any = false;
+   for (int dj = (P.oneD ? 0 : -1); dj <= 0; dj++)
+      for (int di = -1; di <= 0; di++) {
+         int i = vi + di, j = vj + dj;
+         if (!P.periodic && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) continue;
+         if (cellTileActive(P, A.tileMask, A.allActive, i, j)) any = true;
+      }
+   if (!any) return;
+   size_t gv = (size_t)(vj + YO) * P.pitch + (vi + XO);
+   double psib = 1.0 - P.BedPorosity;
+   double rhs;
+   auto emd = [&](int i, int j) -> double {
+      if (!P.periodic && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) return 0.0;
+      if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
+      return A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
+   };
+   if (!P.oneD) {
+      double b0c, btc, bx[4], by[4];
+      centreTopoGlobal(P, A.b0v, A.btk, vi - 1, vj - 1, b0c, btc, bx[0], by[0]);
+      centreTopoGlobal(P, A.b0v, A.btk, vi - 1, vj, b0c, btc, bx[1], by[1]);
+      centreTopoGlobal(P, A.b0v, A.btk, vi, vj - 1, b0c, btc, bx[2], by[2]);
+      centreTopoGlobal(P, A.b0v, A.btk, vi, vj, b0c, btc, bx[3], by[3]);
+      double dbdx = 0.25 * kahan4(bx[0], bx[1], bx[2], bx[3]);
+      double dbdy = 0.25 * kahan4(by[0], by[1], by[2], by[3]);
+      double gam = gamma2(P, dbdx, dbdy);
+      rhs = -0.25 * gam / psib * kahan4(emd(vi - 1, vj - 1), emd(vi - 1, vj), emd(vi, vj - 1), emd(vi, vj));
+   } else {
+      bool lAct = (P.periodic || vi - 1 >= 0) && cellTileActive(P, A.tileMask, A.allActive, vi - 1, 0);
+      bool rAct = (P.periodic || vi < P.NX) && cellTileActive(P, A.tileMask, A.allActive, vi, 0);
+      double b0c, btc, bxl = 0.0, bxr = 0.0, byd;
+      if (lAct) centreTopoGlobal(P, A.b0v, A.btk, vi - 1, 0, b0c, btc, bxl, byd);
+      if (rAct) centreTopoGlobal(P, A.b0v, A.btk, vi, 0, b0c, btc, bxr, byd);
+      if (lAct && rAct) {
+         double dbdx = 0.5 * (bxl + bxr);
+         double gam = gamma2(P, dbdx, 0.0);
+         rhs = -0.5 * gam * (emd(vi - 1, 0) + emd(vi, 0)) / psib;
+      } else {
+         double dbdx = 0.5 * (lAct ? bxl : bxr);
+         double gam = gamma2(P, dbdx, 0.0);
+         rhs = -0.5 * gam * (lAct ? emd(vi - 1, 0) : emd(vi, 0)) / psib;
+      }
+   }
+   double val;
+   if (A.a0 == 0.0) val = A.bt0[gv] + A.dtMorpho * rhs;
+   else val = A.a0 * A.bt0[gv] + A.a1 * (A.btk[gv] + A.dtMorpho * rhs);
+   A.btn[gv] = fmax(-P.EroDepth, val);
+}
+
+// linear updates of w and Hnpsi from the new bed (TimeStepper.f90:587-610)
+template <int BX, int BY>
+__global__ void __launch_bounds__(BX *BY) morpho_cell_kernel(const DevParams P, const MorphoArgs A) {
+   const int2 bo = A.blockList[blockIdx.x];
+   int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
+   if (ci >= P.NX || cj >= P.NY) return;
+   if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) return;
+   size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+   double b0c, bt0c, bx0, by0, btnc, bxn, byn;
+   centreTopoGlobal(P, A.b0v, A.bt0, ci, cj, b0c, bt0c, bx0, by0);
+   centreTopoGlobal(P, A.b0v, A.btn, ci, cj, b0c, btnc, bxn, byn);
+   double gamold = gamma2(P, bx0, by0), gamnew = gamma2(P, bxn, byn);
+   double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
+   double db = btnc - bt0c;
+   double w = -db / gamnew / gamnew;
+   w = w + btnc;
+   w = w + Hn_old * gamold / gamnew / gamnew;
+   w = w + b0c;
+   A.wn[g] = w;
+   double Hnpsi = -(1.0 - P.BedPorosity) * db / gamnew;
+   Hnpsi = Hnpsi + A.hpsi0[g] * gamold / gamnew;
+   A.hpsin[g] = Hnpsi;
+}
+
+struct CheckArgs {
+   const double *w0, *hpsi0, *w3;
+   const double *b0v, *bt0, *bt3;
+   const uint8_t *tileMask;
+   const int2 *blockList;
+   Ctrl *ctrl;
+   RedistEntry *list;
+   int listCap;
+   int allActive;
+};
+
+// Redistribute.f90:158-198
+__device__ __forceinline__ void excessDeposition(const DevParams &P, double hpsi0, double Hn_old, double gamold, double deltaBt, double &excess) {
+   excess = -(hpsi0 * gamold / (1.0 - P.BedPorosity) - deltaBt);
+   excess = fmax(excess, -(Hn_old * gamold - deltaBt));
+}
+
+// the two checks on the morphodynamic update (TimeStepper.f90:709-753), order-free form:
+// refine = OR over cells; the redistribution list is only used when nothing refined.
+template <int BX, int BY>
+__global__ void __launch_bounds__(BX *BY) morpho_check_kernel(const DevParams P, const CheckArgs A) {
+   const int2 bo = A.blockList[blockIdx.x];
+   int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
+   if (ci >= P.NX || cj >= P.NY) return;
+   if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) return;
+   size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+   const double EPS = 2.220446049250313e-16;
+   double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
+   centreTopoGlobal(P, A.b0v, A.bt0, ci, cj, b0c, bt0c, bx0, by0);
+   centreTopoGlobal(P, A.b0v, A.bt3, ci, cj, b0c, bt3c, bx3, by3);
+   double gamold = gamma2(P, bx0, by0), gamnew = gamma2(P, bx3, by3);
+   double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
+   double Hn_new = computeHn(A.w3[g], b0c, bt3c, gamnew);
+   double deltaBt = bt3c - bt0c;
+   // psiold = intermed0's stored psi (desingularised, HydraulicRHS.f90:847)
+   double Hc = Hn_old < 0.0 ? 0.0 : Hn_old, hs = A.hpsi0[g] < 0.0 ? 0.0 : A.hpsi0[g];
+   double psiold = fmin(2.0 * Hc * hs / (Hc * Hc + fmax(Hc * Hc, P.Hneps * P.Hneps)), P.maxPack);
+   double excess;
+   excessDeposition(P, A.hpsi0[g], Hn_old, gamold, deltaBt, excess);
+   if (excess > EPS && deltaBt > EPS && psiold > -EPS) {
+      if (Hn_old < P.EroCritH || fabs(Hn_new - Hn_old) < P.EroCritH) {
+         int k = atomicAdd(&A.ctrl->nRedist, 1);
+         if (k < A.listCap) { A.list[k].excess = excess; A.list[k].i = ci; A.list[k].j = cj; }
+      } else {
+         A.ctrl->refineMorpho = 1;
+      }
+      return;
+   }
+   if (Hn_old < P.EroCritH) return;
+   double rel = fabs(Hn_new - Hn_old) / fabs(Hn_old);
+   if (rel > 0.1) A.ctrl->refineMorpho = 1;
+}
+
+struct RedistArgs {
+   const double *w0, *hpsi0;
+   double *w3, *hpsi3;
+   const double *b0v, *bt0;
+   double *bt3;
+   const uint8_t *tileMask;
+   const RedistEntry *list;
+   int n;
+   int allActive;
+   Ctrl *ctrl;
+};
+
+// RedistributeGrid / RedistributeCell (Redistribute.f90:203-475): inherently sequential
+// (each correction changes the excess of its neighbours), so one thread walks the sorted list.
+__global__ void morpho_redistribute_kernel(const DevParams P, const RedistArgs A) {
+   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+   const double EPS = 2.220446049250313e-16;
+   const int pitch = P.pitch;
+   auto vix = [&](int vi, int vj) -> size_t {
+      if (P.periodic) { vi = wrapIdx(vi, P.NX, 1); if (!P.oneD) vj = wrapIdx(vj, P.NY, 1); }
+      return (size_t)(vj + YO) * pitch + (vi + XO);
+   };
+   // periodic aliases of a vertex that was just modified (keeps the halo copies current)
+   auto storeBt = [&](int vi, int vj, double val) {
+      A.bt3[vix(vi, vj)] = val;
+      if (P.periodic) {
+         int bi = wrapIdx(vi, P.NX, 1), bj = P.oneD ? 0 : wrapIdx(vj, P.NY, 1);
+         for (int oj = -1; oj <= 1; oj++)
+            for (int oi = -1; oi <= 1; oi++) {
+               if (P.oneD && oj != 0) continue;
+               int ai = bi + oi * P.NX, aj = bj + oj * P.NY;
+               if (ai < -2 || ai > P.NX + 2 || aj < (P.oneD ? 0 : -2) || aj > (P.oneD ? 0 : P.NY + 2)) continue;
+               A.bt3[(size_t)(aj + YO) * pitch + (ai + XO)] = val;
+            }
+      }
+   };
+   for (int e = 0; e < A.n; e++) {
+      int i = A.list[e].i, j = A.list[e].j;
+      size_t g = (size_t)(j + YO) * pitch + (i + XO);
+      double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
+      centreTopoGlobal(P, A.b0v, A.bt0, i, j, b0c, bt0c, bx0, by0);
+      centreTopoGlobal(P, A.b0v, A.bt3, i, j, b0c, bt3c, bx3, by3);
+      double gamold = gamma2(P, bx0, by0);
+      double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
+      double corr;
+      excessDeposition(P, A.hpsi0[g], Hn_old, gamold, bt3c - bt0c, corr);
+      if (!(corr > EPS)) continue;
+      // depositional vertices of the cell (Redistribute.f90:276-302)
+      double b_diff[4] = {0, 0, 0, 0}, sum_b_diff = 0.0;
+      int dvi[4], dvj[4], N = 0;
+      const int oi[4] = {0, 1, 0, 1}, oj[4] = {0, 0, 1, 1};
+      for (int k = 0; k < (P.oneD ? 2 : 4); k++) {
+         size_t v = vix(i + oi[k], j + oj[k]);
+         b_diff[N] = A.bt3[v] - A.bt0[v];
+         if (b_diff[N] > 0.0) { dvi[N] = i + oi[k]; dvj[N] = j + oj[k]; sum_b_diff = sum_b_diff + b_diff[N]; N++; }
+      }
+      if (N == 0) { A.ctrl->refineMorpho = 1; return; }
+      double delta = 4.0 * corr / sum_b_diff;
+      double Hnold = Hn_old < 0.0 ? 0.0 : Hn_old;  // intermed0%u(iHn)
+      double db = bt3c - bt0c;
+      double tol = EPS * A.w3[g] * 10.0;
+      double adjustment = 0.0;
+      double discrepancy = kahan3(Hnold * gamold, -db, corr);
+      if (fabs(discrepancy) < tol) {
+         adjustment = kahan3(tol, -Hnold * gamold, db);
+         adjustment = adjustment * (4.0 / sum_b_diff);
+         adjustment = adjustment - delta;
+         adjustment = fmax(adjustment, 0.0);
+      }
+      double Hg = A.hpsi0[g] * gamold / (1.0 - P.BedPorosity);
+      tol = EPS * 10.0;
+      discrepancy = kahan3(Hg, -db, corr);
+      if (fabs(discrepancy) < tol) {
+         double adj = kahan3(tol, -Hg, db);
+         adj = adj * (4.0 / sum_b_diff);
+         adj = adj - delta;
+         adjustment = fmax(adjustment, adj);
+      }
+      delta = delta + adjustment;
+      for (int k = 0; k < N; k++) {
+         size_t v = vix(dvi[k], dvj[k]);
+         storeBt(dvi[k], dvj[k], A.bt3[v] - delta * b_diff[k]);
+      }
+      // refresh the surrounding 3^D cells (Redistribute.f90:404-472)
+      for (int ci = i - 1; ci <= i + 1; ci++)
+         for (int cj = (P.oneD ? 0 : j - 1); cj <= (P.oneD ? 0 : j + 1); cj++) {
+            if (!P.periodic && (ci < 0 || ci >= P.NX || cj < 0 || cj >= P.NY)) continue;
+            int wi = wrapIdx(ci, P.NX, P.periodic), wj = P.oneD ? 0 : wrapIdx(cj, P.NY, P.periodic);
+            if (!cellTileActive(P, A.tileMask, A.allActive, wi, wj)) continue;
+            size_t gc = (size_t)(wj + YO) * pitch + (wi + XO);
+            double c_b0, c_bt0, c_bx0, c_by0, c_bt3, c_bx3, c_by3;
+            centreTopoGlobal(P, A.b0v, A.bt0, wi, wj, c_b0, c_bt0, c_bx0, c_by0);
+            centreTopoGlobal(P, A.b0v, A.bt3, wi, wj, c_b0, c_bt3, c_bx3, c_by3);
+            double dbc = c_bt3 - c_bt0;
+            double go = gamma2(P, c_bx0, c_by0), gn = gamma2(P, c_bx3, c_by3);
+            double Ho = computeHn(A.w0[gc], c_b0, c_bt0, go);
+            if (Ho < 0.0) Ho = 0.0;
+            double w;
+            if (!P.oneD) {
+               w = c_bt3;
+               w = w + (Ho * go / gn - dbc / gn) / gn;
+               w = w + c_b0;
+            } else {
+               w = -dbc / gn / gn;
+               w = w + Ho * go / gn / gn;
+               w = w + c_bt3;
+               w = w + c_b0;
+            }
+            A.w3[gc] = w;
+            A.hpsi3[gc] = A.hpsi0[gc] * go / gn - (1.0 - P.BedPorosity) * dbc / gn;
+         }
+   }
+}
+
 }  // namespace kgpu

@@ -1,6 +1,151 @@
-// Strang remainder M(2dt) H(dt) of one step (TimeStepper.f90:194-255); included by kestrel_gpu.cu.
+// kgpu_morpho_host.inl -- Strang remainder M(2 dt) . H(dt) of one step
+// (TimeStepper.f90:194-255, 532-781); included by kestrel_gpu.cu after hydraulicTimeStepper.
+//
+// Buffers on entry (first H done): S[ib] = result of H1, S[ia] = its momenta before the
+// implicit correction.  M stages alternate between S[ic] and S[id] (w and Hnpsi planes only;
+// the momenta do not change over M).  The second H runs q0' = S[ic] -> result S[id].
+
+__global__ void ctrl_morpho_reset_kernel(Ctrl *c) {
+   c->refineMorpho = 0;
+   c->nRedist = 0;
+}
+
+static int fillHaloPlanes(kgpu_handle *h, double *const *planes, int n, bool vertices) {
+   if (!h->periodic) return 0;
+   HaloArgs a;
+   a.nf = n;
+   for (int d = 0; d < n; d++) a.f[d] = planes[d];
+   int ex = vertices ? 1 : 0;
+   if (!h->oneD) {
+      halo_periodic_x_kernel<<<(h->NY + ex + 127) / 128, 128, 0, h->stream>>>(h->D, a, ex);
+      halo_periodic_y_kernel<<<(h->NX + 4 + ex + 127) / 128, 128, 0, h->stream>>>(h->D, a, ex);
+      h->launches += 2;
+   } else {
+      halo_periodic_x_kernel<<<1, 32, 0, h->stream>>>(h->D, a, ex);
+      h->launches += 1;
+   }
+   return 0;
+}
+
+template <bool ONED>
+static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
+   constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
+   morpho_emd_kernel<BX, BY><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, a);
+   dim3 gv((h->NX + 1 + 127) / 128, h->oneD ? 1 : h->NY + 1);
+   morpho_bed_kernel<<<gv, 128, 0, h->stream>>>(h->D, a);
+   double *pl[1] = {a.btn};
+   int rc = fillHaloPlanes(h, pl, 1, true);
+   if (rc) return rc;
+   morpho_cell_kernel<BX, BY><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, a);
+   double *pc[2] = {a.wn, a.hpsin};
+   rc = fillHaloPlanes(h, pc, 2, false);
+   h->launches += 3;
+   CUDA_TRY(h, cudaGetLastError());
+   return rc;
+}
+
 static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &again) {
-   (void)t0; (void)dt_hydro; again = false;
-   h->err = "morphodynamics not available in this build";
-   return KGPU_ERR_UNSUPPORTED;
+   again = false;
+   int rc;
+   const int R1 = h->ib, PRE = h->ia, MA = h->ic, MB = h->id;
+   const int allAct = h->allActive() ? 1 : 0;
+   int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
+   if (h->nBlocks == 0) return 0;
+   // halo of the H1 result (w, Hnpsi are read with a 1-cell stencil by the dry-neighbour test)
+   if ((rc = fillHaloCells(h, R1))) return rc;
+   // velocities frozen over M = those of H1's 4th RHS evaluation (pre-correction momenta)
+   if (h->oneD)
+      morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
+                                                                            h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
+   else
+      morpho_prepare_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
+                                                                            h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
+   h->launches++;
+   double dt_morpho = 2.0 * dt_hydro;
+   MorphoArgs a;
+   a.w0 = h->S[R1][QW]; a.hpsi0 = h->S[R1][QHPSI]; a.U = h->Um; a.V = h->Vm; a.b0v = h->b0v; a.bt0 = h->btv[h->bt0];
+   a.EmD = h->EmD; a.tileMask = h->d_tileMask; a.blockList = h->d_blockList; a.ctrl = h->d_ctrl; a.allActive = allAct;
+   a.dtMorpho = dt_morpho;
+   // stage 1 (TimeStepper.f90:566-610)
+   a.w = h->S[R1][QW]; a.hpsi = h->S[R1][QHPSI]; a.btk = h->btv[h->bt0]; a.btn = h->btv[h->bt1];
+   a.wn = h->S[MA][QW]; a.hpsin = h->S[MA][QHPSI]; a.a0 = 0.0; a.a1 = 1.0;
+   if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
+   // stage 2 (:612-655)
+   a.w = h->S[MA][QW]; a.hpsi = h->S[MA][QHPSI]; a.btk = h->btv[h->bt1]; a.btn = h->btv[h->bt2];
+   a.wn = h->S[MB][QW]; a.hpsin = h->S[MB][QHPSI]; a.a0 = 0.75; a.a1 = 0.25;
+   if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
+   // stage 3 (:657-699)
+   a.w = h->S[MB][QW]; a.hpsi = h->S[MB][QHPSI]; a.btk = h->btv[h->bt2]; a.btn = h->btv[h->bt3];
+   a.wn = h->S[MA][QW]; a.hpsin = h->S[MA][QHPSI]; a.a0 = 1.0 / 3.0; a.a1 = 2.0 / 3.0;
+   if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
+   // checks (:709-753)
+   ctrl_morpho_reset_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl);
+   CheckArgs c;
+   c.w0 = h->S[R1][QW]; c.hpsi0 = h->S[R1][QHPSI]; c.w3 = h->S[MA][QW]; c.b0v = h->b0v; c.bt0 = h->btv[h->bt0]; c.bt3 = h->btv[h->bt3];
+   c.tileMask = h->d_tileMask; c.blockList = h->d_blockList; c.ctrl = h->d_ctrl; c.list = h->d_redist; c.listCap = h->redistCap; c.allActive = allAct;
+   if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, c);
+   else morpho_check_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, c);
+   h->launches += 2;
+   if ((rc = readCtrl(h))) return rc;
+   bool refine = h->h_ctrl->refineMorpho != 0;
+   int nRed = h->h_ctrl->nRedist;
+   if (!refine && nRed > h->redistCap) refine = true;  // list overflow: treat like a failed redistribution
+   if (!refine && nRed > 0) {
+      // sorted ascending by excess, ties in scan order: active-tile order, then j, then i (Redistribute.f90:69-101)
+      CUDA_TRY(h, cudaMemcpyAsync(h->h_redist, h->d_redist, sizeof(RedistEntry) * nRed, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      int nX = h->nX, nY = h->nY, nXt = h->nXt;
+      std::stable_sort(h->h_redist, h->h_redist + nRed, [&](const RedistEntry &x, const RedistEntry &y) {
+         if (x.excess != y.excess) return x.excess < y.excess;
+         int tx_ = (x.i / nX) + (x.j / nY) * nXt, ty_ = (y.i / nX) + (y.j / nY) * nXt;
+         if (tx_ != ty_) return tx_ < ty_;
+         if (x.j != y.j) return x.j < y.j;
+         return x.i < y.i;
+      });
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_redist, h->h_redist, sizeof(RedistEntry) * nRed, cudaMemcpyHostToDevice, h->stream));
+      RedistArgs r;
+      r.w0 = h->S[R1][QW]; r.hpsi0 = h->S[R1][QHPSI]; r.w3 = h->S[MA][QW]; r.hpsi3 = h->S[MA][QHPSI];
+      r.b0v = h->b0v; r.bt0 = h->btv[h->bt0]; r.bt3 = h->btv[h->bt3]; r.tileMask = h->d_tileMask; r.list = h->d_redist; r.n = nRed;
+      r.allActive = allAct; r.ctrl = h->d_ctrl;
+      morpho_redistribute_kernel<<<1, 32, 0, h->stream>>>(h->D, r);
+      h->launches++;
+      if ((rc = readCtrl(h))) return rc;
+      refine = h->h_ctrl->refineMorpho != 0;
+   }
+   if (refine) {
+      // newdt = dt_morpho/2, dt_hydro = newdt/2 (TimeStepper.f90:762-773, 203-214)
+      dt_morpho = 0.5 * dt_morpho;
+      dt_hydro = 0.5 * dt_morpho;
+      h->nrefines++;
+      again = true;
+      return 0;
+   }
+   // state after M = (w3, rhoHnu, rhoHnv, Hnpsi3): momenta are those of H1
+   size_t fb = h->fieldElems * sizeof(double);
+   CUDA_TRY(h, cudaMemcpyAsync(h->S[MA][QHU], h->S[R1][QHU], fb, cudaMemcpyDeviceToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(h->S[MA][QHV], h->S[R1][QHV], fb, cudaMemcpyDeviceToDevice, h->stream));
+   // second hydraulic operator (TimeStepper.f90:217-254); grid%t = t0 + dt_hydro
+   double tNow = t0 + dt_hydro;
+   if ((rc = firstRHS(h, MA, h->bt3, tNow, 0.0, 0))) return rc;
+   h->e0Valid = false;
+   if ((rc = readCtrl(h))) return rc;
+   double advised = h->h_ctrl->dtAdvised;
+   if (advised < dt_hydro) {
+      if ((dt_hydro - advised) / dt_hydro < 0.1) dt_hydro = 0.9 * dt_hydro;
+      else dt_hydro = advised;
+      h->nrefines++;
+      again = true;
+      return 0;
+   }
+   ctrl_set_dt_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, dt_hydro);
+   h->launches++;
+   if ((rc = hydraulicTimeStepper(h, MA, h->ia, MB, h->bt3))) return rc;
+   if (h->h_ctrl->nonfinite) { h->err = "non-finite state"; return KGPU_ERR_DT; }
+   if (h->h_ctrl->failed) {
+      dt_hydro = h->h_ctrl->dtNew;
+      h->nrefines++;
+      again = true;
+      return 0;
+   }
+   return 0;
 }

@@ -35,7 +35,11 @@ struct StatePtrs {
 
 // SetDefaultTileData / SetDomainBoundaryData / ActivateTile's "w = b0" (UpdateTiles.f90:342-370, 595-664).
 // kind: 0 = default ghost data into every state buffer, 1 = dirichlet ghost, 2 = activation (w = b0c in S0 only)
-__global__ void tile_default_kernel(const DevParams P, StatePtrs S0, StatePtrs SA, StatePtrs SB, const double *b0v,
+struct AllStates {
+   double *q[5][4];
+   int n;  // buffers in use; q[0] is the current state
+};
+__global__ void tile_default_kernel(const DevParams P, AllStates S, const double *b0v,
                                     const double *btv, int tx, int ty, int kind, double bcH, double bcU, double bcV, double bcPsi) {
    int li = blockIdx.x * blockDim.x + threadIdx.x;
    int lj = blockIdx.y;
@@ -45,7 +49,7 @@ __global__ void tile_default_kernel(const DevParams P, StatePtrs S0, StatePtrs S
    double b0c, btc, bx, by;
    centreTopoGlobal(P, b0v, btv, ci, cj, b0c, btc, bx, by);
    if (kind == 2) {
-      S0.q[QW][g] = b0c;
+      S.q[0][QW][g] = b0c;
       return;
    }
    double w = b0c, hu = 0.0, hv = 0.0, hpsi = 0.0;
@@ -56,9 +60,8 @@ __global__ void tile_default_kernel(const DevParams P, StatePtrs S0, StatePtrs S
       w = w + b0c;
       hu = rho * bcH * bcU; hv = rho * bcH * bcV; hpsi = bcH * bcPsi;
    }
-   StatePtrs *all[3] = {&S0, &SA, &SB};
-   for (int k = 0; k < 3; k++) {
-      all[k]->q[QW][g] = w; all[k]->q[QHU][g] = hu; all[k]->q[QHV][g] = hv; all[k]->q[QHPSI][g] = hpsi;
+   for (int k = 0; k < S.n; k++) {
+      S.q[k][QW][g] = w; S.q[k][QHU][g] = hu; S.q[k][QHV][g] = hv; S.q[k][QHPSI][g] = hpsi;
    }
 }
 

@@ -121,8 +121,9 @@ def test_2d_flux_source_dynamic_tiles(oracle_lib, gpu_lib):
     """tests/Input_flux_hydro_2d.txt shortened: flux source, halt BC, tile activation; active set
     must match bit-exactly and the delivered volume must be conserved to 1e-10."""
     path = os.path.join(INPUTS, "case_flux_hydro_2d.txt")
-    sg = run_input(gpu_lib, path, tend=4.0, Nout=2, nXpertile=10, nYpertile=10, nXtiles=60, nYtiles=60, Xtilesize=10.0)
-    so = run_input(oracle_lib, path, tend=4.0, Nout=2, nXpertile=10, nYpertile=10, nXtiles=60, nYtiles=60, Xtilesize=10.0)
+    kw = dict(tend=6.0, Nout=2, nXpertile=20, nYpertile=20, nXtiles=40, nYtiles=40, Xtilesize=20.0, TileBuffer=6)
+    sg = run_input(gpu_lib, path, **kw)
+    so = run_input(oracle_lib, path, **kw)
     assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
     assert len(sg.stepper.active_tiles()) > len(sg.ic_tiles)
     res = compare_snapshots(sg.snapshots[-1], so.snapshots[-1])
@@ -142,7 +143,7 @@ def test_halt_boundary_error_code(gpu_lib):
     from kestrel_b200 import capi
     path = os.path.join(INPUTS, "case_1d_cap_constslope.txt")
     with pytest.raises(capi.KestrelError) as ei:
-        run_input(gpu_lib, path, nXtiles=4, tend=200.0, Nout=1)
+        run_input(gpu_lib, path, nXtiles=5, tend=200.0, Nout=1)
     assert ei.value.code == capi.KGPU_ERR_HALT_BC
 
 
@@ -162,3 +163,52 @@ def test_full_size_properties(gpu_lib):
     assert info.nsteps == 40
     assert abs(vol1 - vol0) / vol0 < 1e-10
     assert np.min(q[0] - b0c) >= -1e-14
+
+
+# ------------------------------------------------------------------ morphodynamics (Strang split)
+MORPHO_TOL = 1e-10  # libdevice tanh/log/pow differ from glibc by <= 1-2 ulp
+
+
+def test_morpho_dambreak_periodic(oracle_lib, gpu_lib):
+    """H(dt) M(2dt) H(dt) with Variable drag, Mixed erosion, Spearman-Manning deposition."""
+    rs = dambreak_runset(2, 32, morpho=True)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io = so.integrate_to(1e9, 15)
+    ig = sg.integrate_to(1e9, 15)
+    assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
+    assert abs(io.t - ig.t) <= 1e-12 * io.t
+    (qo, bo), (qg, bg) = so.download_domain(True), sg.download_domain(True)
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert rel_linf(qg[d], qo[d]) <= MORPHO_TOL, name
+    assert np.max(np.abs(bo)) > 1e-6, "the bed must have moved for this test to mean anything"
+    assert rel_linf(bg, bo) <= MORPHO_TOL
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("case_cap_morpho.txt", dict(tend=4.0, Nout=2)),
+    ("case_flat_depositional.txt", dict(tend=2.0, Nout=1)),
+    ("case_lake_at_rest_morpho_2d.txt", dict(tend=1.0, Nout=1)),
+    ("case_cap_morpho_2d.txt", dict(tend=0.6, Nout=1, nXtiles=12, nYtiles=12)),
+])
+def test_morpho_reference_inputs(oracle_lib, gpu_lib, case, kw):
+    """Reference morphodynamic test inputs (shortened): fields to 1e-10, identical active sets,
+    identical step / rollback counts, erosion depth bound, non-negative depth."""
+    path = os.path.join(INPUTS, case)
+    sg = run_input(gpu_lib, path, **kw)
+    so = run_input(oracle_lib, path, **kw)
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert (sg.infos[-1].nsteps, sg.infos[-1].nrefines) == (so.infos[-1].nsteps, so.infos[-1].nrefines)
+    res = compare_snapshots(sg.snapshots[-1], so.snapshots[-1])
+    for name, (err, exact) in res.items():
+        assert err <= MORPHO_TOL, f"{name}: {err}"
+    for k, tile in sg.snapshots[-1].items():
+        assert rel_linf(tile["bt"], so.snapshots[-1][k]["bt"]) <= MORPHO_TOL or np.max(np.abs(so.snapshots[-1][k]["bt"])) == 0
+        assert tile["u"][..., 4].min() >= -1e-14
+        assert tile["bt"].min() >= -sg.rs.EroDepth
+    # solids are conserved: flow solids + bed solids (Volume.txt columns 6 + 7)
+    v0, vn = sg.volume_rows[0], sg.volume_rows[-1]
+    tot0, totn = v0[5] + v0[6], vn[5] + vn[6]
+    if tot0 > 0:
+        assert abs(totn - tot0) / tot0 < 1e-10
