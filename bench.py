@@ -157,7 +157,7 @@ def main():
 
     import torch
     from kestrel_b200 import capi
-    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
+    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state, decomposition, rank_block
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,10 +176,22 @@ def main():
     while need > 0.9 * free_b and size > 1024:
         size //= 2
         need = 30 * (size + 64) ** 2 * 8
-    rs = dambreak_runset(size // 128, 128)
+    # weak scaling: every GPU owns a size x size block of a (px*size) x (py*size) periodic domain
+    px, py = decomposition(world)
+    T = size // 128
+    rs = dambreak_runset(T, 128)
+    if world > 1:
+        rs.nXtiles, rs.nYtiles = px * T, py * T
+        rs.Ytilesize = None
+        rs.finalize()
+        from kestrel_b200.host.settings import Cube
+        Lx, Ly = rs.xSize, rs.ySize
+        rs.cubes = [Cube(x=0.0, y=0.0, length=Lx, width=Ly, height=1.0, psi=0.0, shape="level"),
+                    Cube(x=-0.25 * Lx, y=0.0, length=0.5 * Lx, width=Ly, height=1.0, psi=0.0, shape="flat")]
+        rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
     rs.device = local_rank
-    cells = rs.NX * rs.NY
-    q4_np, b0v_np = dambreak_state(rs)
+    cells = size * size
+    q4_np, b0v_np = dambreak_state(rs, rank_block(rs, rank, px, py) if world > 1 else None)
     # pinned host buffers (the Fortran host's arrays stand-in) for the e2e leg
     q4 = torch.from_numpy(q4_np).pin_memory()
     b0v = torch.from_numpy(b0v_np).pin_memory()
@@ -188,6 +200,17 @@ def main():
 
     p, keep = rs.to_c()
     st = capi.Stepper(lib, p, keep)
+    if world > 1:  # ncclUniqueId from rank 0, broadcast by the host's own means (torch.distributed)
+        n = lib.comm_id_bytes()
+        idt = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            hb = (capi.C.c_ubyte * n)()
+            assert lib.comm_create_id(hb) == 0
+            idt.copy_(torch.tensor(list(hb), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        idb = (capi.C.c_ubyte * n)(*idt.cpu().tolist())
+        rc = lib.comm_attach(st.h, idb)
+        assert rc == 0, lib.last_error(st.h)
     st.upload_domain(q4.numpy(), b0v.numpy())
     stream = torch.cuda.ExternalStream(lib.stream(st.h))
 
@@ -272,6 +295,8 @@ def main():
                 "config": {"workload": "synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off, all tiles active "
                                        "(BASELINE.json configs[4])",
                            "cells_per_gpu": cells, "grid": f"{rs.NX}x{rs.NY}", "tiles": f"{rs.nXtiles}x{rs.nYtiles} of 128x128",
+                           "decomposition": f"{px}x{py} blocks, 2-cell halos by ncclSend/ncclRecv overlapped with the interior, "
+                                            "one ncclAllReduce(min) per dt decision" if world > 1 else "single device",
                            "arithmetic": "faithful fp64 (no FMA contraction)", "l2": "fields are 2.1 GB each >> 126 MB L2; no flush needed",
                            "rolled_back_attempts": nref},
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

@@ -129,6 +129,10 @@ typedef struct kgpu_params {
    int32_t device;             /* CUDA device ordinal; -1 = current device */
    int32_t arithmetic;         /* 0 = faithful (no FMA contraction, reference operation order);
                                   1 = contracted (FMA + shared reciprocals), validated to 1e-10 */
+   /* 2-D block decomposition of the tile grid over comm_size = comm_px*comm_py processes
+      (one per GPU).  comm_size <= 1: single device.  Rank r owns tile columns
+      [r%px * nXtiles/px, ...) and tile rows [r/px * nYtiles/py, ...).                     */
+   int32_t comm_rank, comm_size, comm_px, comm_py;
 } kgpu_params;
 
 typedef struct kgpu_handle kgpu_handle;
@@ -203,10 +207,15 @@ int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices);
 int kgpu_comm_id_bytes(void);
 /* Rank 0 creates the id; the host broadcasts it to all ranks by its own means. */
 int kgpu_comm_create_id(void *id_out);
-/* Call between kgpu_create and the first upload.  The handle then owns tiles
- * [tx0, tx0+ntx) x [ty0, ty0+nty) of the global tile grid (0-based), plus halos. */
-int kgpu_comm_attach(kgpu_handle *h, const void *id, int32_t rank, int32_t nranks,
-                     int32_t px, int32_t py);
+/* Call between kgpu_create (with comm_* set in the params) and the first upload; collective
+ * over all ranks.  With a communicator attached, kgpu_upload_domain / kgpu_download_domain
+ * take the rank's own block (local NX x NY cells, (NX+1) x (NY+1) vertices); 2-cell halos of
+ * the four primary fields move by ncclSend/ncclRecv after every stage, overlapped with the
+ * interior of the stage kernel, and one ncclAllReduce(min) per dt decision keeps every rank
+ * on the same time step.  Round 1: periodic, all tiles active, hydraulic operator only.   */
+int kgpu_comm_attach(kgpu_handle *h, const void *id);
+/* Tile block owned by this handle (0-based global tile coordinates). */
+int kgpu_comm_block(kgpu_handle *h, int32_t *tx0, int32_t *ty0, int32_t *ntx, int32_t *nty);
 
 /* ---- introspection ------------------------------------------------------------ */
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */

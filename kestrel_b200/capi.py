@@ -74,6 +74,7 @@ class KgpuParams(C.Structure):
         ("heights", HEIGHTS_FN),
         ("heights_ctx", C.c_void_p),
         ("device", C.c_int32), ("arithmetic", C.c_int32),
+        ("comm_rank", C.c_int32), ("comm_size", C.c_int32), ("comm_px", C.c_int32), ("comm_py", C.c_int32),
     ]
 
 
@@ -130,7 +131,8 @@ class Library:
             ("stream", C.c_void_p, [C.c_void_p]),
             ("comm_id_bytes", C.c_int, []),
             ("comm_create_id", C.c_int, [C.c_void_p]),
-            ("comm_attach", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+            ("comm_attach", C.c_int, [C.c_void_p, C.c_void_p]),
+            ("comm_block", C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
             ("set_pinned", C.c_int, [C.c_void_p, C.c_int32]),
         ]:
             try:
@@ -173,6 +175,8 @@ class Stepper:
             raise KestrelError(rc, "create failed (is a CUDA device visible?)" if lib.prefix == "kgpu_" else "create failed")
         self.nX, self.nY = params.nXpertile, params.nYpertile
         self.nXt, self.nYt = params.nXtiles, params.nYtiles
+        if params.comm_size > 1:  # this handle owns one block of the tile grid
+            self.nXt, self.nYt = params.nXtiles // params.comm_px, params.nYtiles // params.comm_py
         self.NX, self.NY = self.nX * self.nXt, self.nY * self.nYt
         self.oneD = bool(params.isOneD)
 

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "kgpu_comm.cuh"
 #include "kgpu_hydro.cuh"
 #include "kgpu_morpho.cuh"
 #include "kgpu_tiles.cuh"
@@ -38,6 +39,17 @@ constexpr int BX1 = 128, BY1 = 1;  // 1-D stage tile
 const double HUGE_D = std::numeric_limits<double>::max();
 }  // namespace
 
+// 2-D block decomposition over NCCL ranks (one process per GPU)
+struct kgpu_comm {
+   bool active = false;
+   int rank = 0, size = 1, px = 1, py = 1, rx = 0, ry = 0;
+   int west = -1, east = -1, south = -1, north = -1;  // neighbour ranks (-1: none / local wrap)
+   void *nccl = nullptr;
+   double *sendBuf[4] = {}, *recvBuf[4] = {};
+   cudaStream_t stream = nullptr;       // communication stream
+   cudaEvent_t evBoundary = nullptr, evHalo = nullptr;
+};
+
 struct kgpu_handle {
    kgpu_params P;
    DevParams D;
@@ -48,6 +60,11 @@ struct kgpu_handle {
 
    int NX = 0, NY = 0, nX = 0, nY = 0, nXt = 0, nYt = 0, nTiles = 0, pitch = 0, rows = 0;
    bool oneD = false, periodic = false, morpho = false;
+   bool globalPeriodic = false;  // bcs = periodic on the whole domain; `periodic` = this device wraps onto itself
+   kgpu_comm comm;
+   int gtx0 = 0, gty0 = 0, gnXt = 0, gnYt = 0;
+   int2 *d_blockBoundary = nullptr, *d_blockInterior = nullptr;
+   int nBoundary = 0, nInterior = 0;
    size_t fieldElems = 0;
 
    // device fields
@@ -162,7 +179,11 @@ static int refreshMasks(kgpu_handle *h) {
       for (int tx = -1; tx <= h->nXt; tx++) {
          int sx = tx, sy = ty;
          if (h->periodic) { sx = (tx + h->nXt) % h->nXt; sy = (ty + h->nYt) % h->nYt; }
-         if (sx < 0 || sx >= h->nXt || sy < 0 || sy >= h->nYt) continue;
+         if (sx < 0 || sx >= h->nXt || sy < 0 || sy >= h->nYt) {
+            // ring tile owned by a neighbouring rank: decomposed runs keep every tile active
+            if (h->comm.active && h->globalPeriodic) mask[(size_t)(ty + 1) * mw + tx + 1] = 2;
+            continue;
+         }
          int t0 = sy * h->nXt + sx;
          mask[(size_t)(ty + 1) * mw + tx + 1] = (uint8_t)h->tstate[t0];
          srcm[(size_t)(ty + 1) * mw + tx + 1] = (uint8_t)h->hasSource[t0];
@@ -185,6 +206,15 @@ static int refreshMasks(kgpu_handle *h) {
       }
    h->nBlocks = (int)list.size();
    if (h->nBlocks) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockList, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+   if (h->comm.active) {
+      // blocks touching the edge of the local domain are computed first so that their strips can travel
+      // while the interior is still being computed
+      std::vector<int2> bnd, inr;
+      for (const int2 &b : list) ((b.x == 0 || b.x == nbx - 1 || b.y == 0 || b.y == nby - 1) ? bnd : inr).push_back(b);
+      h->nBoundary = (int)bnd.size(); h->nInterior = (int)inr.size();
+      if (h->nBoundary) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockBoundary, bnd.data(), bnd.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+      if (h->nInterior) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockInterior, inr.data(), inr.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+   }
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
    h->masksDirty = false;
    return 0;
@@ -192,7 +222,11 @@ static int refreshMasks(kgpu_handle *h) {
 
 // periodic wrap of the halo (single device).  Non-periodic domains need nothing: the
 // cells around the active region are static ghost data.
+static int exchangeHalo(kgpu_handle *h, double *const *planes, int nf, bool vertices, cudaStream_t s);
+static int allreduceCfl(kgpu_handle *h, int slot);
+
 static int fillHaloCells(kgpu_handle *h, int k) {
+   if (h->comm.active) return exchangeHalo(h, h->S[k], 4, false, h->stream);
    if (!h->periodic) return 0;
    HaloArgs a; a.nf = 4;
    for (int d = 0; d < 4; d++) a.f[d] = h->S[k][d];
@@ -207,6 +241,7 @@ static int fillHaloCells(kgpu_handle *h, int k) {
    return 0;
 }
 static int fillHaloVertices(kgpu_handle *h, double *v) {
+   if (h->comm.active) { double *pl[1] = {v}; return exchangeHalo(h, pl, 1, true, h->stream); }
    if (!h->periodic) return 0;
    HaloArgs a; a.nf = 1; a.f[0] = v;
    if (!h->oneD) {
@@ -221,16 +256,18 @@ static int fillHaloVertices(kgpu_handle *h, double *v) {
 }
 
 template <bool ONED>
-static void launchStageT(kgpu_handle *h, const StageArgs &a) {
+static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
+   if (nblocks <= 0) return;
    if (h->morpho) {
       size_t sm = G::smemBytes(true);
-      hydro_stage_kernel<BX, BY, ONED, true><<<h->nBlocks, BX * BY, sm, h->stream>>>(h->D, a);
+      hydro_stage_kernel<BX, BY, ONED, true><<<nblocks, BX * BY, sm, h->stream>>>(h->D, a);
    } else {
       size_t sm = G::smemBytes(false);
-      hydro_stage_kernel<BX, BY, ONED, false><<<h->nBlocks, BX * BY, sm, h->stream>>>(h->D, a);
+      hydro_stage_kernel<BX, BY, ONED, false><<<nblocks, BX * BY, sm, h->stream>>>(h->D, a);
    }
+   h->launches++;
 }
 
 // One fused RHS(+stage update) launch.  mode: StageMode; qin / qout = state buffer indices
@@ -251,7 +288,22 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
    a.mode = mode;
    a.allActive = h->allActive() ? 1 : 0;
    if (h->timeRhs) cudaEventRecord(h->evA, h->stream);
-   if (h->oneD) launchStageT<true>(h, a); else launchStageT<false>(h, a);
+   bool overlap = h->comm.active && mode != MODE_RHS;
+   if (!overlap) {
+      if (h->oneD) launchStageT<true>(h, a, h->nBlocks); else launchStageT<false>(h, a, h->nBlocks);
+   } else {
+      // edge blocks first; their strips travel on the communication stream while the interior runs
+      a.blockList = h->d_blockBoundary;
+      if (h->oneD) launchStageT<true>(h, a, h->nBoundary); else launchStageT<false>(h, a, h->nBoundary);
+      CUDA_TRY(h, cudaEventRecord(h->comm.evBoundary, h->stream));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->comm.stream, h->comm.evBoundary, 0));
+      int rc = exchangeHalo(h, h->S[kout], 4, false, h->comm.stream);
+      if (rc) return rc;
+      CUDA_TRY(h, cudaEventRecord(h->comm.evHalo, h->comm.stream));
+      a.blockList = h->d_blockInterior;
+      if (h->oneD) launchStageT<true>(h, a, h->nInterior); else launchStageT<false>(h, a, h->nInterior);
+      CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->comm.evHalo, 0));
+   }
    if (h->timeRhs) {
       cudaEventRecord(h->evB, h->stream);
       cudaEventSynchronize(h->evB);
@@ -260,8 +312,9 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
       h->rhsMs += ms;
       h->rhsLaunches++;
    }
-   h->launches++;
    CUDA_TRY(h, cudaGetLastError());
+   // single device: the periodic image of what was just written
+   if (!overlap && mode != MODE_RHS) return fillHaloCells(h, kout);
    return 0;
 }
 
@@ -449,11 +502,11 @@ static double nextFluxSeriesTime(const kgpu_handle *h, double t) {
 // =========================================================================== the step
 // substep-1 RHS of state kin -> E0, I0 and the advised dt (HydraulicRHS.f90:64-174)
 static int firstRHS(kgpu_handle *h, int kin, int kbt, double tNow, double tmax, int setDt) {
-   int rc = fillHaloCells(h, kin);
-   if (rc) return rc;
+   int rc;
    ctrl_begin_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl, tNow);
    rc = launchStage(h, MODE_RHS, kin, -1, kin, kbt);
    if (rc) return rc;
+   if ((rc = allreduceCfl(h, 0))) return rc;
    ctrl_advise_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, h->allActive() ? 0 : 1, tmax, setDt);
    h->launches += 2;
    return 0;
@@ -476,11 +529,11 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    int rc;
    if ((rc = fillHaloCells(h, ka))) return rc;
    if ((rc = launchStage(h, MODE_STAGE2, ka, kb, kq0, kbt))) return rc;
+   if ((rc = allreduceCfl(h, 1))) return rc;
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 1);
-   if ((rc = fillHaloCells(h, kb))) return rc;
    if ((rc = launchStage(h, MODE_STAGE3, kb, ka, kq0, kbt))) return rc;
+   if ((rc = allreduceCfl(h, 2))) return rc;
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 2);
-   if ((rc = fillHaloCells(h, ka))) return rc;
    if ((rc = launchStage(h, MODE_FINAL, ka, kb, kq0, kbt))) return rc;
    h->launches += 2;
    // maxima on the state at the start of the whole step (tileContainer), stamped t + dt (quirk Q1)
@@ -498,6 +551,7 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    return readCtrl(h);
 }
 
+#include "kgpu_comm_host.inl"
 #include "kgpu_morpho_host.inl"
 
 static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_info *info) {
@@ -507,7 +561,10 @@ static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_
    int rc;
    while (integrating) {
       if ((rc = checkIfNearBoundaries(h))) return rc;
-      if ((rc = refreshMasks(h))) return rc;
+      if (h->masksDirty) {  // tile data changed: refresh the wrapped image of the current state
+         if ((rc = refreshMasks(h))) return rc;
+         if ((rc = fillHaloCells(h, h->i0))) return rc;
+      }
       double t0 = h->t;
       double tmax = std::min(tend, nextFluxSeriesTime(h, h->t));
       if ((rc = firstRHS(h, h->i0, h->bt0, h->t, tmax, h->morpho ? 2 : 1))) return rc;
@@ -587,6 +644,12 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
    cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
+   cudaFree(h->d_blockBoundary); cudaFree(h->d_blockInterior);
+   for (int k = 0; k < 4; k++) { cudaFree(h->comm.sendBuf[k]); cudaFree(h->comm.recvBuf[k]); }
+   if (h->comm.nccl && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->comm.nccl);
+   if (h->comm.evBoundary) cudaEventDestroy(h->comm.evBoundary);
+   if (h->comm.evHalo) cudaEventDestroy(h->comm.evHalo);
+   if (h->comm.stream) cudaStreamDestroy(h->comm.stream);
    if (h->evA) cudaEventDestroy(h->evA);
    if (h->evB) cudaEventDestroy(h->evB);
    if (h->stream) cudaStreamDestroy(h->stream);
@@ -614,8 +677,29 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       h->src.push_back(S);
    }
    h->nX = p->nXpertile; h->nY = p->nYpertile; h->nXt = p->nXtiles; h->nYt = p->nYtiles;
+   h->gnXt = p->nXtiles; h->gnYt = p->nYtiles;
+   h->oneD = p->isOneD != 0; h->globalPeriodic = p->bcs == KGPU_BC_PERIODIC; h->morpho = p->MorphodynamicsOn != 0;
+   h->periodic = h->globalPeriodic;
+   if (p->comm_size > 1) {
+      kgpu_comm &c = h->comm;
+      c.size = p->comm_size; c.rank = p->comm_rank; c.px = p->comm_px; c.py = p->comm_py;
+      bool okc = c.px >= 1 && c.py >= 1 && c.px * c.py == c.size && c.rank >= 0 && c.rank < c.size &&
+                 p->nXtiles % c.px == 0 && p->nYtiles % c.py == 0 && !(h->oneD && c.py != 1);
+      if (!okc || h->morpho || !h->globalPeriodic) {
+         fprintf(stderr, "kgpu_create: decomposition needs px*py = size, tiles divisible by px, py, periodic bcs and the "
+                         "hydraulic operator only (round 1)\n");
+         delete h;
+         return okc ? KGPU_ERR_UNSUPPORTED : KGPU_ERR_ARG;
+      }
+      c.rx = c.rank % c.px; c.ry = c.rank / c.px;
+      h->nXt = p->nXtiles / c.px; h->nYt = p->nYtiles / c.py;
+      h->gtx0 = c.rx * h->nXt; h->gty0 = c.ry * h->nYt;
+      auto rk = [&](int x, int y) { return ((y + c.py) % c.py) * c.px + ((x + c.px) % c.px); };
+      if (c.px > 1) { c.west = rk(c.rx - 1, c.ry); c.east = rk(c.rx + 1, c.ry); }
+      if (c.py > 1) { c.south = rk(c.rx, c.ry - 1); c.north = rk(c.rx, c.ry + 1); }
+      h->periodic = false;  // the local block does not wrap onto itself (per direction handled in exchangeHalo)
+   }
    h->NX = h->nX * h->nXt; h->NY = h->nY * h->nYt; h->nTiles = h->nXt * h->nYt;
-   h->oneD = p->isOneD != 0; h->periodic = p->bcs == KGPU_BC_PERIODIC; h->morpho = p->MorphodynamicsOn != 0;
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
    h->pitch = roundUp(XO + roundUp(h->NX, BX) + 8, 16);
    h->rows = h->oneD ? (YO + 1 + 3) : (YO + roundUp(h->NY, BY) + 4);
@@ -624,7 +708,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    DevParams &D = h->D;
    std::memset(&D, 0, sizeof(D));
    D.NX = h->NX; D.NY = h->NY; D.nX = h->nX; D.nY = h->nY; D.nXt = h->nXt; D.nYt = h->nYt;
-   D.gtx0 = 0; D.gty0 = 0; D.gnXt = h->nXt; D.gnYt = h->nYt;
+   D.gtx0 = h->gtx0; D.gty0 = h->gty0; D.gnXt = h->gnXt; D.gnYt = h->gnYt;
    D.pitch = h->pitch; D.rows = h->rows;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
    D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;
@@ -668,6 +752,8 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    int nbx = (h->NX + BX - 1) / BX, nby = (h->NY + BY - 1) / BY;
    if (cudaMalloc(&h->d_tileMask, msz) != cudaSuccess || cudaMalloc(&h->d_tileSource, msz) != cudaSuccess) return fail("masks");
    if (cudaMalloc(&h->d_blockList, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess) return fail("blocklist");
+   if (p->comm_size > 1 && (cudaMalloc(&h->d_blockBoundary, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess ||
+                            cudaMalloc(&h->d_blockInterior, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess)) return fail("blocklists");
    if (cudaMalloc(&h->d_ctrl, sizeof(Ctrl)) != cudaSuccess || cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)) != cudaSuccess) return fail("ctrl");
    cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), h->stream);
    std::memset(h->h_ctrl, 0, sizeof(Ctrl));
@@ -744,7 +830,8 @@ int kgpu_upload_tile(kgpu_handle *h, int32_t tile_id, const double *u13, const d
 
 int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertices, const double *bt_vertices) {
    if (!h || !q4 || !b0_vertices) return KGPU_ERR_ARG;
-   if (!h->periodic) { h->err = "kgpu_upload_domain needs Boundary Conditions = periodic (UpdateTiles.f90:61-69)"; return KGPU_ERR_ARG; }
+   if (!h->globalPeriodic) { h->err = "kgpu_upload_domain needs Boundary Conditions = periodic (UpdateTiles.f90:61-69)"; return KGPU_ERR_ARG; }
+   if (h->P.comm_size > 1 && !h->comm.active) { h->err = "call kgpu_comm_attach before uploading"; return KGPU_ERR_ARG; }
    cudaSetDevice(h->dev);
    size_t nc = (size_t)h->NX * h->NY;
    size_t dp = (size_t)h->pitch * sizeof(double);
@@ -766,6 +853,8 @@ int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertic
    h->masksDirty = true;
    h->firstScan = false;
    h->havePre = false;
+   if ((rc = refreshMasks(h))) return rc;
+   if ((rc = fillHaloCells(h, h->i0))) return rc;
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
    return KGPU_OK;
 }
@@ -779,7 +868,10 @@ int kgpu_integrate_to(kgpu_handle *h, double tend, int64_t max_steps, kgpu_step_
 int kgpu_active_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
    if (!h || !n) return KGPU_ERR_ARG;
    *n = (int32_t)h->activeList.size();
-   if (ids) for (size_t k = 0; k < h->activeList.size(); k++) ids[k] = h->activeList[k];
+   if (ids) for (size_t k = 0; k < h->activeList.size(); k++) {
+      int t0 = h->activeList[k] - 1;
+      ids[k] = (h->gty0 + t0 / h->nXt) * h->gnXt + h->gtx0 + t0 % h->nXt + 1;
+   }
    return KGPU_OK;
 }
 int kgpu_ghost_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
@@ -841,6 +933,7 @@ int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, doubl
    cudaSetDevice(h->dev);
    int rc;
    if ((rc = refreshMasks(h))) return rc;
+   if ((rc = fillHaloCells(h, h->i0))) return rc;
    if ((rc = firstRHS(h, h->i0, h->bt0, h->t, HUGE_D, 0))) return rc;
    if ((rc = readCtrl(h))) return rc;
    size_t nc = (size_t)h->NX * h->NY;
@@ -857,8 +950,48 @@ int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, doubl
    return KGPU_OK;
 }
 
-int kgpu_comm_id_bytes(void) { return 128; }
-int kgpu_comm_create_id(void *) { return KGPU_ERR_UNSUPPORTED; }
-int kgpu_comm_attach(kgpu_handle *, const void *, int32_t, int32_t, int32_t, int32_t) { return KGPU_ERR_UNSUPPORTED; }
+int kgpu_comm_id_bytes(void) { return (int)sizeof(ncclUniqueId); }
+
+int kgpu_comm_create_id(void *id_out) {
+   std::string err;
+   if (!id_out || !loadNccl(err)) { fprintf(stderr, "kgpu_comm_create_id: %s\n", err.c_str()); return KGPU_ERR_CUDA; }
+   ncclUniqueId id;
+   if (g_nccl.GetUniqueId(&id) != ncclSuccess) return KGPU_ERR_CUDA;
+   std::memcpy(id_out, &id, sizeof(id));
+   return KGPU_OK;
+}
+
+int kgpu_comm_attach(kgpu_handle *h, const void *id_in) {
+   if (!h || !id_in) return KGPU_ERR_ARG;
+   if (h->P.comm_size <= 1) { h->err = "params.comm_size <= 1: nothing to attach"; return KGPU_ERR_ARG; }
+   cudaSetDevice(h->dev);
+   if (!loadNccl(h->err)) return KGPU_ERR_CUDA;
+   ncclUniqueId id;
+   std::memcpy(&id, id_in, sizeof(id));
+   ncclComm_t comm;
+   NCCL_TRY(h, g_nccl.CommInitRank(&comm, h->comm.size, id, h->comm.rank));
+   h->comm.nccl = comm;
+   size_t nx = (size_t)4 * (h->NY + 1) * 2, ny = (size_t)4 * (h->NX + 5) * 2;
+   for (int k = 0; k < 4; k++) {
+      size_t n = (k < 2 ? nx : ny) * sizeof(double);
+      CUDA_TRY(h, cudaMalloc(&h->comm.sendBuf[k], n));
+      CUDA_TRY(h, cudaMalloc(&h->comm.recvBuf[k], n));
+   }
+   CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm.stream, cudaStreamNonBlocking));
+   CUDA_TRY(h, cudaEventCreateWithFlags(&h->comm.evBoundary, cudaEventDisableTiming));
+   CUDA_TRY(h, cudaEventCreateWithFlags(&h->comm.evHalo, cudaEventDisableTiming));
+   h->comm.active = true;
+   h->masksDirty = true;
+   return KGPU_OK;
+}
+
+int kgpu_comm_block(kgpu_handle *h, int32_t *tx0, int32_t *ty0, int32_t *ntx, int32_t *nty) {
+   if (!h) return KGPU_ERR_ARG;
+   if (tx0) *tx0 = h->gtx0;
+   if (ty0) *ty0 = h->gty0;
+   if (ntx) *ntx = h->nXt;
+   if (nty) *nty = h->nYt;
+   return KGPU_OK;
+}
 
 }  // extern "C"

@@ -51,8 +51,7 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    const int allAct = h->allActive() ? 1 : 0;
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
    if (h->nBlocks == 0) return 0;
-   // halo of the H1 result (w, Hnpsi are read with a 1-cell stencil by the dry-neighbour test)
-   if ((rc = fillHaloCells(h, R1))) return rc;
+   // (the halo of the H1 result was produced together with it)
    // velocities frozen over M = those of H1's 4th RHS evaluation (pre-correction momenta)
    if (h->oneD)
       morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
@@ -126,6 +125,7 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    CUDA_TRY(h, cudaMemcpyAsync(h->S[MA][QHV], h->S[R1][QHV], fb, cudaMemcpyDeviceToDevice, h->stream));
    // second hydraulic operator (TimeStepper.f90:217-254); grid%t = t0 + dt_hydro
    double tNow = t0 + dt_hydro;
+   if ((rc = fillHaloCells(h, MA))) return rc;  // redistribution may have touched cells after the stage halo
    if ((rc = firstRHS(h, MA, h->bt3, tNow, 0.0, 0))) return rc;
    h->e0Valid = false;
    if ((rc = readCtrl(h))) return rc;

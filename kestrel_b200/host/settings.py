@@ -130,6 +130,10 @@ class RunSet:
     # library options
     arithmetic: int = 0
     device: int = -1
+    comm_rank: int = 0
+    comm_size: int = 1
+    comm_px: int = 1
+    comm_py: int = 1
 
     # ---- derived (DomainSettings.f90:173-225)
     def finalize(self) -> "RunSet":
@@ -215,4 +219,5 @@ class RunSet:
             p.heights = cb
         p.device = self.device
         p.arithmetic = self.arithmetic
+        p.comm_rank, p.comm_size, p.comm_px, p.comm_py = self.comm_rank, self.comm_size, self.comm_px, self.comm_py
         return p, keep

@@ -36,28 +36,36 @@ def dambreak_runset(n_tiles: int, per_tile: int = 128, morpho: bool = False, **o
     return rs
 
 
-def dambreak_state(rs: RunSet):
-    """Flat-domain initial state: q4[(4, NY, NX)] = (w, rhoHnu, rhoHnv, Hnpsi) and b0v[(NY+1, NX+1)].
-    Same arithmetic as LoadSourceConditions on every cell (SetSources.f90:305-355), evaluated on the
-    whole domain at once (row blocks keep the temporaries small at 16384^2)."""
-    NX, NY = rs.NX, rs.NY
-    xv = -0.5 * rs.xSize + rs.deltaX * np.arange(NX + 1, dtype=np.float64)
-    yv = -0.5 * rs.ySize + rs.deltaY * np.arange(NY + 1, dtype=np.float64)
+def dambreak_state(rs: RunSet, block=None):
+    """Initial state of the whole domain, or of one block of the tile grid.
+
+    Returns q4[(4, NY, NX)] = (w, rhoHnu, rhoHnv, Hnpsi) and b0v[(NY+1, NX+1)] for the cells
+    [i0, i0+NX) x [j0, j0+NY) of the global grid; block = (tx0, ty0, ntx, nty) in tiles (the
+    2-D decomposition of kgpu_comm_attach), None = everything.  Same arithmetic as
+    LoadSourceConditions on every cell (SetSources.f90:305-355); row blocks keep the
+    temporaries small at 16384^2.  Periodic: global vertex NX aliases vertex 0
+    (EqualiseTopographicBoundaryData across the wrap), so vertex coordinates wrap."""
+    NXg, NYg = rs.NX, rs.NY
+    if block is None:
+        i0, j0, NX, NY = 0, 0, NXg, NYg
+    else:
+        tx0, ty0, ntx, nty = block
+        i0, j0, NX, NY = tx0 * rs.nXpertile, ty0 * rs.nYpertile, ntx * rs.nXpertile, nty * rs.nYpertile
+    xv = -0.5 * rs.xSize + rs.deltaX * ((i0 + np.arange(NX + 1)) % NXg).astype(np.float64)
+    yv = -0.5 * rs.ySize + rs.deltaY * ((j0 + np.arange(NY + 1)) % NYg).astype(np.float64)
     q4 = np.zeros((4, NY, NX))
     b0v = np.empty((NY + 1, NX + 1))
     rows = max(1, min(NY, (1 << 22) // max(NX, 1)))
-    for j0 in range(0, NY + 1, rows):
-        j1 = min(NY + 1, j0 + rows)
-        b0v[j0:j1] = topog(rs, xv, yv[j0:j1])
-    # periodic: vertex NX aliases vertex 0 (EqualiseTopographicBoundaryData across the wrap)
-    b0v[:, NX] = b0v[:, 0]
-    b0v[NY, :] = b0v[0, :]
-    x = xv[:-1] + 0.5 * rs.deltaX
-    for j0 in range(0, NY, rows):
-        j1 = min(NY, j0 + rows)
-        b0c, _, bx, by = centre_topography(rs, b0v[j0:j1 + 1])
+    for r0 in range(0, NY + 1, rows):
+        r1 = min(NY + 1, r0 + rows)
+        b0v[r0:r1] = topog(rs, xv, yv[r0:r1])
+    x = -0.5 * rs.xSize + rs.deltaX * (i0 + np.arange(NX)).astype(np.float64) + 0.5 * rs.deltaX
+    yc = -0.5 * rs.ySize + rs.deltaY * (j0 + np.arange(NY)).astype(np.float64) + 0.5 * rs.deltaY
+    for r0 in range(0, NY, rows):
+        r1 = min(NY, r0 + rows)
+        b0c, _, bx, by = centre_topography(rs, b0v[r0:r1 + 1])
         gam = gamma(rs, bx, by)
-        y = yv[j0:j1] + 0.5 * rs.deltaY
+        y = yc[r0:r1]
         w = b0c.copy()
         hpsi = np.zeros_like(w)
         X = x[None, :] + 0.0 * y[:, None]
@@ -73,6 +81,17 @@ def dambreak_state(rs: RunSet):
             else:
                 w[m] += (cube.height / gam)[m]
                 hpsi[m] += cube.psi * cube.height
-        q4[0, j0:j1] = w
-        q4[3, j0:j1] = hpsi
+        q4[0, r0:r1] = w
+        q4[3, r0:r1] = hpsi
     return q4, b0v
+
+
+def decomposition(n: int):
+    """(px, py) of the 2-D block decomposition used for n GPUs."""
+    return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}.get(n) or (n, 1)
+
+
+def rank_block(rs: RunSet, rank: int, px: int, py: int):
+    """Tile block (tx0, ty0, ntx, nty) owned by `rank` -- the rule of kgpu_create."""
+    ntx, nty = rs.nXtiles // px, rs.nYtiles // py
+    return ((rank % px) * ntx, (rank // px) * nty, ntx, nty)
