@@ -92,8 +92,7 @@ class ClockSampler:
 def oracle_library():
     from kestrel_b200 import capi
     path = os.path.join(ROOT, "oracle", "libkestrel_oracle.so")
-    if not os.path.exists(path):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)  # no-op when up to date
     return capi.Library(path, "kor_")
 
 

@@ -18,8 +18,7 @@ def oracle_lib():
     """The CPU oracle (test infrastructure only)."""
     from kestrel_b200 import capi
     path = os.path.join(ROOT, "oracle", "libkestrel_oracle.so")
-    if not os.path.exists(path):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])  # no-op when up to date
     return capi.Library(path, "kor_")
 
 
@@ -27,8 +26,7 @@ def oracle_lib():
 def oracle_fma_lib():
     from kestrel_b200 import capi
     path = os.path.join(ROOT, "oracle", "libkestrel_oracle_fma.so")
-    if not os.path.exists(path):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])  # no-op when up to date
     return capi.Library(path, "kor_")
 
 

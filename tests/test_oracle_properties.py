@@ -1,0 +1,159 @@
+"""The reference's own property tests (tests/runall.jl, tests/testlib.jl) re-expressed against
+the CPU oracle.  The reference ships no golden vectors, so these properties -- plus the
+line-by-line citations in oracle/kestrel_oracle.cpp -- are what pins the oracle:
+
+  test_flow_consistency  = conservation (rel. err <= 1e-10, testlib.jl:106-158)
+                           and positivity (Hn >= -1e-14, :286-302)
+                           and erosion-depth bound (bt >= -EroDepth, :306-328)
+  check_no_flow          = lake at rest: every (x, Hn) pair printed with 10 digits must appear in
+                           the initial output (:332-358)
+  check_identical_simulations = tile-layout independence to 1e-13 / 1e-11 (runall.jl:45-46)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import INPUTS, run_input
+from kestrel_b200.host.inputfile import read_input_file
+
+RTOL = 1e-10
+
+
+def integrate_source_time_series(t, Q, psi, tstart, tend):
+    """testlib.jl:224-282."""
+    total, solids = 0.0, 0.0
+    if len(t) == 1 and t[0] < tend:
+        duration = min(tend - tstart, tend - t[0])
+        total = Q[0] * duration
+        solids = psi[0] * total
+    for i in range(len(t) - 1):
+        if t[i + 1] < tstart or t[i] > tend:
+            continue
+        dQ = (Q[i + 1] - Q[i]) / (t[i + 1] - t[i])
+        dp = (psi[i + 1] - psi[i]) / (t[i + 1] - t[i])
+        tl, tu, Ql, Qu, pl, pu = t[i], t[i + 1], Q[i], Q[i + 1], psi[i], psi[i + 1]
+        if t[i] < tstart:
+            tl, Ql, pl = tstart, Q[i] + dQ * (tstart - t[i]), psi[i] + dp * (tstart - t[i])
+        if t[i + 1] > tend:
+            tu, Qu, pu = tend, Q[i] + dQ * (tend - t[i]), psi[i] + dp * (tend - t[i])
+        dt = tu - tl
+        total += dt * (Ql + Qu) / 2
+        solids += (dt / 6) * (Ql * pu + Qu * pl + 2 * (Ql * pl + Qu * pu))
+    return total, solids
+
+
+def check_flow_consistency(sim):
+    rs = sim.rs
+    flux_vol = flux_sol = 0.0
+    for s in rs.sources:
+        a, b = integrate_source_time_series(s.time, s.flux, s.psi, rs.tstart, rs.tend)
+        flux_vol += a
+        flux_sol += b
+    v0, vn = sim.volume_rows[0], sim.volume_rows[-1]
+    expected = flux_vol + v0[1] + v0[2]
+    final = vn[1] + vn[2]
+    assert abs((expected - final) / expected) <= RTOL, ("volume", expected, final)
+    exp_sol = flux_sol + (v0[5] + v0[6]) / rs.rhos
+    fin_sol = (vn[5] + vn[6]) / rs.rhos
+    if exp_sol == 0.0:
+        assert abs(exp_sol - fin_sol) <= RTOL
+    else:
+        assert abs((exp_sol - fin_sol) / exp_sol) <= RTOL, ("solids", exp_sol, fin_sol)
+    for snap in sim.snapshots:
+        for tile in snap.values():
+            assert tile["u"][..., 4].min() >= -1e-14          # positivity
+            assert tile["u"][..., 10].min() >= -rs.EroDepth    # max erosion depth
+
+
+ONE_D = ["flat_depositional", "cap_dilute", "cap_conc", "cap_morpho", "flux_hydro", "flux_edwards2019", "flux_morpho"]
+
+
+@pytest.mark.parametrize("case", ONE_D)
+def test_flow_consistency_1d(oracle_lib, case):
+    """runall.jl:4-12, full length."""
+    check_flow_consistency(run_input(oracle_lib, os.path.join(INPUTS, f"case_{case}.txt")))
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("flux_hydro_2d", dict(tend=3.0, Nout=1)),
+    ("cap_morpho_2d", dict(tend=1.0, Nout=1)),
+    ("flat_depositional_2d", dict()),
+])
+def test_flow_consistency_2d(oracle_lib, case, kw):
+    """runall.jl:14-23, shortened so the CPU suite stays within minutes."""
+    check_flow_consistency(run_input(oracle_lib, os.path.join(INPUTS, f"case_{case}.txt"), **kw))
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("lake_at_rest_hydro", dict(tend=1.0, Nout=2)),
+    ("lake_at_rest_hydro_2d", dict()),
+    ("lake_at_rest_morpho", dict()),
+    ("lake_at_rest_morpho_2d", dict()),
+])
+def test_no_flow(oracle_lib, case, kw):
+    """runall.jl:25-30 / check_no_flow: printed (x, Hn) pairs never change."""
+    sim = run_input(oracle_lib, os.path.join(INPUTS, f"case_{case}.txt"), **kw)
+    first = sim.snapshots[0]
+    for snap in sim.snapshots[1:]:
+        assert sorted(snap) == sorted(first)
+        for k in first:
+            a = np.char.mod("%18.10E", first[k]["u"][..., 4])
+            b = np.char.mod("%18.10E", snap[k]["u"][..., 4])
+            assert np.array_equal(a, b)
+
+
+def test_tile_independence_static(oracle_lib):
+    """runall.jl:32-47: the same flow on 100 m and 50 m tiles agrees to 1e-13 (Hn, u, Hnpsi, bt)."""
+    a = run_input(oracle_lib, os.path.join(INPUTS, "case_tile_indep_static_100m.txt"), tend=1.0, Nout=1)
+    b = run_input(oracle_lib, os.path.join(INPUTS, "case_tile_indep_static_50m.txt"), tend=1.0, Nout=1)
+
+    def flat(sim):
+        rs = sim.rs
+        out = np.zeros((4, rs.NY, rs.NX))
+        for tid, t in sim.snapshots[-1].items():
+            tx, ty = (tid - 1) % rs.nXtiles, (tid - 1) // rs.nXtiles
+            sl = (slice(ty * rs.nYpertile, (ty + 1) * rs.nYpertile), slice(tx * rs.nXpertile, (tx + 1) * rs.nXpertile))
+            for n, d in enumerate([4, 5, 3, 10]):
+                out[n][sl] = t["u"][..., d]
+        return out
+
+    A, B = flat(a), flat(b)
+    # same dx, both domains centred on the origin: B is a centred window of A; cells of inactive
+    # tiles are dry (zero) in either layout
+    oy, ox = (A.shape[1] - B.shape[1]) // 2, (A.shape[2] - B.shape[2]) // 2
+    assert a.rs.deltaX == b.rs.deltaX and ox >= 0 and oy >= 0
+    A = A[:, oy:oy + B.shape[1], ox:ox + B.shape[2]]
+    assert np.max(np.abs(A - B)) <= 1e-13
+    assert np.max(np.abs(A[0])) > 0.01
+
+
+def test_normalised_inputs_roundtrip(tmp_path):
+    """write_input_file(read_input_file(x)) is a fixed point (the fixtures in tests/inputs/)."""
+    from kestrel_b200.host.inputfile import write_input_file
+    for name in ["case_cap_morpho_2d.txt", "case_flux_morpho.txt", "case_lake_at_rest_hydro_2d.txt"]:
+        rs = read_input_file(os.path.join(INPUTS, name))
+        out = tmp_path / name
+        write_input_file(rs, str(out))
+        rs2 = read_input_file(str(out))
+        for k in ("nXtiles", "nYtiles", "nXpertile", "deltaX", "bcs", "drag", "erosion", "cfl", "heightThreshold", "tend",
+                  "EroRate", "EroDepth", "topog_func", "topog_params", "TileBuffer", "CriticalShields", "ws0"):
+            assert getattr(rs, k) == getattr(rs2, k), k
+        assert len(rs.caps) == len(rs2.caps) and len(rs.sources) == len(rs2.sources)
+
+
+def test_fma_contraction_band(oracle_lib, oracle_fma_lib):
+    """How far the reference's own answer moves under FMA contraction (gfortran -O2 -march=native
+    contracts): the honest floor under the 1e-10 parity criterion."""
+    from common import domain_stepper, rel_linf
+    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
+    rs = dambreak_runset(2, 32)
+    q4, b0v = dambreak_state(rs)
+    a = domain_stepper(oracle_lib, rs, q4, b0v)
+    b = domain_stepper(oracle_fma_lib, rs, q4, b0v)
+    a.integrate_to(1e9, 60)
+    b.integrate_to(1e9, 60)
+    qa, qb = a.download_domain(), b.download_domain()
+    errs = [rel_linf(qb[d], qa[d]) for d in range(4)]
+    print("rel-Linf faithful vs FMA-contracted oracle after 60 steps:", errs)
+    assert max(errs) < 1e-9
