@@ -34,7 +34,8 @@ using namespace kgpu;
    } while (0)
 
 namespace {
-constexpr int BX2 = 32, BY2 = 8;   // 2-D stage tile (256 threads)
+constexpr int BX2 = 32, BY2 = 7;   // 2-D stage tile: 224 cells, 487 faces = 2 passes of 256 threads
+constexpr int NTHREADS = 256;
 constexpr int BX1 = 128, BY1 = 1;  // 1-D stage tile
 const double HUGE_D = std::numeric_limits<double>::max();
 }  // namespace
@@ -80,6 +81,8 @@ struct kgpu_handle {
    int bt0 = 0, bt1 = 1, bt2 = 2, bt3 = 3;
    double *EBt = nullptr, *EmD = nullptr;
    double *mx[11] = {};
+   TopoPlanes topo = {};       // precomputed cell / face topography for the stage kernel
+   int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
 
    uint8_t *d_tileMask = nullptr, *d_tileSource = nullptr;
@@ -217,6 +220,7 @@ static int refreshMasks(kgpu_handle *h) {
    }
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
    h->masksDirty = false;
+   h->topoBtIdx = -1;  // new blocks need their planes
    return 0;
 }
 
@@ -255,19 +259,31 @@ static int fillHaloVertices(kgpu_handle *h, double *v) {
    return 0;
 }
 
-template <bool ONED>
-static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
+template <bool ONED, bool HASBT, int LIM>
+static void launchStageK(kgpu_handle *h, const StageArgs &a, int nblocks) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM><<<nblocks, NTHREADS, G::smemBytes(), h->stream>>>(h->D, a);
+}
+template <bool ONED>
+static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
    if (nblocks <= 0) return;
-   if (h->morpho) {
-      size_t sm = G::smemBytes(true);
-      hydro_stage_kernel<BX, BY, ONED, true><<<nblocks, BX * BY, sm, h->stream>>>(h->D, a);
-   } else {
-      size_t sm = G::smemBytes(false);
-      hydro_stage_kernel<BX, BY, ONED, false><<<nblocks, BX * BY, sm, h->stream>>>(h->D, a);
-   }
+   const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
+   if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, true, -1>(h, a, nblocks); }
+   else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, false, -1>(h, a, nblocks); }
    h->launches++;
+}
+
+// (Re)compute the topography planes from the vertex arrays for every listed block.
+static int computeTopo(kgpu_handle *h, int kbt) {
+   if (h->nBlocks == 0) return 0;
+   const double *btv = h->morpho ? h->btv[kbt] : nullptr;
+   if (h->oneD) topo_planes_kernel<BX1, BY1, true><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList);
+   else topo_planes_kernel<BX2, BY2, false><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList);
+   h->launches++;
+   h->topoBtIdx = kbt;
+   CUDA_TRY(h, cudaGetLastError());
+   return 0;
 }
 
 // One fused RHS(+stage update) launch.  mode: StageMode; qin / qout = state buffer indices
@@ -281,8 +297,8 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
       a.qout[d] = (mode == MODE_RHS) ? h->E0[d] : h->S[kout][d];
    }
    a.Iout = h->I0;
-   a.b0v = h->b0v;
-   a.btv = h->morpho ? h->btv[kbt] : nullptr;
+   a.T = h->topo;
+   if (h->topoBtIdx != kbt) { int rct = computeTopo(h, kbt); if (rct) return rct; }
    a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
    a.ctrl = h->d_ctrl; a.sources = h->d_sources;
    a.mode = mode;
@@ -373,6 +389,7 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
    int rc = fillHaloVertices(h, h->b0v);
    if (rc) return rc;
    h->loaded[t0] = 1;
+   h->topoBtIdx = -1;
    // ghost tiles sharing the refreshed seam keep w = b0 at the cell centre
    int tW = tileW(h, t0), tS = h->oneD ? -1 : tileS(h, t0);
    int tSW = (tW >= 0 && !h->oneD) ? tileS(h, tW) : -1;
@@ -522,8 +539,8 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    for (int d = 0; d < 4; d++) { u.q0[d] = h->S[kq0][d]; u.E[d] = h->E0[d]; u.q1[d] = h->S[ka][d]; }
    u.I = h->I0; u.tileMask = h->d_tileMask; u.blockList = h->d_blockList; u.ctrl = h->d_ctrl; u.allActive = h->allActive() ? 1 : 0;
    if (h->nBlocks) {
-      if (h->oneD) stage1_update_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, u);
-      else stage1_update_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, u);
+      if (h->oneD) stage1_update_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, u);
+      else stage1_update_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, u);
       h->launches++;
    }
    int rc;
@@ -540,10 +557,10 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    if (h->nBlocks) {
       const double *btm = h->morpho ? h->btv[h->bt0] : nullptr;
       if (h->oneD)
-         maxima_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
+         maxima_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
                                                                        h->d_blockList, h->d_ctrl, u.allActive);
       else
-         maxima_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
+         maxima_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
                                                                        h->d_blockList, h->d_ctrl, u.allActive);
       h->launches++;
    }
@@ -573,6 +590,7 @@ static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_
       int guard = 0, kres = h->ib;
       while (true) {
          if (++guard > 200) { h->err = "time step underflow (200 refinements of one step)"; return KGPU_ERR_DT; }
+         if (h->morpho && h->topoBtIdx != h->bt0 && (rc = computeTopo(h, h->bt0))) return rc;
          if (!h->e0Valid) {  // E0/I0 were reused by the second H operator: re-evaluate (rare)
             if ((rc = firstRHS(h, h->i0, h->bt0, t0, tmax, 0))) return rc;
             h->e0Valid = true;
@@ -644,6 +662,11 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
    cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
+   {
+      double *pl[15] = {h->topo.b0c, h->topo.bxc, h->topo.byc, h->topo.gamc, h->topo.xb0, h->topo.xB, h->topo.xtan, h->topo.xgam,
+                        h->topo.yb0, h->topo.yB, h->topo.ytan, h->topo.ygam, h->topo.btc, h->topo.xbt, h->topo.ybt};
+      for (int k = 0; k < 15; k++) cudaFree(pl[k]);
+   }
    cudaFree(h->d_blockBoundary); cudaFree(h->d_blockInterior);
    for (int k = 0; k < 4; k++) { cudaFree(h->comm.sendBuf[k]); cudaFree(h->comm.recvBuf[k]); }
    if (h->comm.nccl && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->comm.nccl);
@@ -770,10 +793,24 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
           cudaMallocHost(&h->h_redist, sizeof(RedistEntry) * h->redistCap) != cudaSuccess) return fail("redist");
    }
    // opt in to > 48 KB dynamic shared memory for the stage kernel
-   cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX2, BY2, false>::smemBytes(false));
-   cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX2, BY2, false>::smemBytes(true));
-   cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX1, BY1, true>::smemBytes(false));
-   cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageGeom<BX1, BY1, true>::smemBytes(true));
+   {
+      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes();
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+   }
+   // topography planes (bt planes only when the bed moves)
+   {
+      double **pl[15] = {&h->topo.b0c, &h->topo.bxc, &h->topo.byc, &h->topo.gamc, &h->topo.xb0, &h->topo.xB, &h->topo.xtan, &h->topo.xgam,
+                         &h->topo.yb0, &h->topo.yB, &h->topo.ytan, &h->topo.ygam, &h->topo.btc, &h->topo.xbt, &h->topo.ybt};
+      int npl = h->morpho ? 15 : 12;
+      for (int k = 0; k < npl; k++) if (!allocField(pl[k], 0.0)) return fail("topography planes");
+   }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;
    return KGPU_OK;

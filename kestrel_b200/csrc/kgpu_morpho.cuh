@@ -54,9 +54,10 @@ __device__ __forceinline__ double storedHn(const DevParams &P, const double *w, 
 
 // velocities of the hydraulic result as its 4th RHS evaluation left them (pre-correction momenta)
 template <int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) morpho_prepare_kernel(const DevParams P, const double *w, const double *hpsi, const double *huPre,
+__global__ void __launch_bounds__(256) morpho_prepare_kernel(const DevParams P, const double *w, const double *hpsi, const double *huPre,
                                                                 const double *hvPre, const double *b0v, const double *btv, double *U,
                                                                 double *V, const uint8_t *tileMask, const int2 *blockList, int allActive) {
+   if (threadIdx.x >= BX * BY) return;
    const int2 bo = blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
    if (ci >= P.NX || cj >= P.NY) return;
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(BX *BY) morpho_prepare_kernel(const DevParams 
 
 // CalculateMorphodynamicRHS, cell part (MorphodynamicRHS.f90:96-145)
 template <int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) morpho_emd_kernel(const DevParams P, const MorphoArgs A) {
+__global__ void __launch_bounds__(256) morpho_emd_kernel(const DevParams P, const MorphoArgs A) {
+   if (threadIdx.x >= BX * BY) return;
    const int2 bo = A.blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
    if (ci >= P.NX || cj >= P.NY) return;
@@ -146,7 +148,8 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
 
 // linear updates of w and Hnpsi from the new bed (TimeStepper.f90:587-610)
 template <int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) morpho_cell_kernel(const DevParams P, const MorphoArgs A) {
+__global__ void __launch_bounds__(256) morpho_cell_kernel(const DevParams P, const MorphoArgs A) {
+   if (threadIdx.x >= BX * BY) return;
    const int2 bo = A.blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
    if (ci >= P.NX || cj >= P.NY) return;
@@ -188,7 +191,8 @@ __device__ __forceinline__ void excessDeposition(const DevParams &P, double hpsi
 // the two checks on the morphodynamic update (TimeStepper.f90:709-753), order-free form:
 // refine = OR over cells; the redistribution list is only used when nothing refined.
 template <int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) morpho_check_kernel(const DevParams P, const CheckArgs A) {
+__global__ void __launch_bounds__(256) morpho_check_kernel(const DevParams P, const CheckArgs A) {
+   if (threadIdx.x >= BX * BY) return;
    const int2 bo = A.blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
    if (ci >= P.NX || cj >= P.NY) return;

@@ -30,13 +30,13 @@ static int fillHaloPlanes(kgpu_handle *h, double *const *planes, int n, bool ver
 template <bool ONED>
 static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
-   morpho_emd_kernel<BX, BY><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, a);
+   morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
    dim3 gv((h->NX + 1 + 127) / 128, h->oneD ? 1 : h->NY + 1);
    morpho_bed_kernel<<<gv, 128, 0, h->stream>>>(h->D, a);
    double *pl[1] = {a.btn};
    int rc = fillHaloPlanes(h, pl, 1, true);
    if (rc) return rc;
-   morpho_cell_kernel<BX, BY><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, a);
+   morpho_cell_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
    double *pc[2] = {a.wn, a.hpsin};
    rc = fillHaloPlanes(h, pc, 2, false);
    h->launches += 3;
@@ -54,10 +54,10 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    // (the halo of the H1 result was produced together with it)
    // velocities frozen over M = those of H1's 4th RHS evaluation (pre-correction momenta)
    if (h->oneD)
-      morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
+      morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
                                                                             h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
    else
-      morpho_prepare_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
+      morpho_prepare_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
                                                                             h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
    h->launches++;
    double dt_morpho = 2.0 * dt_hydro;
@@ -82,8 +82,8 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    CheckArgs c;
    c.w0 = h->S[R1][QW]; c.hpsi0 = h->S[R1][QHPSI]; c.w3 = h->S[MA][QW]; c.b0v = h->b0v; c.bt0 = h->btv[h->bt0]; c.bt3 = h->btv[h->bt3];
    c.tileMask = h->d_tileMask; c.blockList = h->d_blockList; c.ctrl = h->d_ctrl; c.list = h->d_redist; c.listCap = h->redistCap; c.allActive = allAct;
-   if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, c);
-   else morpho_check_kernel<BX2, BY2><<<h->nBlocks, BX * BY, 0, h->stream>>>(h->D, c);
+   if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
+   else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    h->launches += 2;
    if ((rc = readCtrl(h))) return rc;
    bool refine = h->h_ctrl->refineMorpho != 0;
@@ -126,6 +126,7 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    // second hydraulic operator (TimeStepper.f90:217-254); grid%t = t0 + dt_hydro
    double tNow = t0 + dt_hydro;
    if ((rc = fillHaloCells(h, MA))) return rc;  // redistribution may have touched cells after the stage halo
+   if ((rc = computeTopo(h, h->bt3))) return rc;  // the bed moved: new cell / face topography for the second H
    if ((rc = firstRHS(h, MA, h->bt3, tNow, 0.0, 0))) return rc;
    h->e0Valid = false;
    if ((rc = readCtrl(h))) return rc;

@@ -99,10 +99,11 @@ struct MaximaPtrs {
    double *Hnmax, *HnmaxT, *umax, *umaxT, *emax, *emaxT, *dmax, *dmaxT, *psimax, *psimaxT, *tfirst;
 };
 template <int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) maxima_kernel(const DevParams P, StatePtrs S0, const double *b0v, const double *btv,
+__global__ void __launch_bounds__(256) maxima_kernel(const DevParams P, StatePtrs S0, const double *b0v, const double *btv,
                                                         MaximaPtrs M, const uint8_t *tileMask, const int2 *blockList,
                                                         const Ctrl *ctrl, int allActive) {
    if (ctrl->failed) return;
+   if (threadIdx.x >= BX * BY) return;
    const int2 bo = blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
    if (ci >= P.NX || cj >= P.NY) return;
