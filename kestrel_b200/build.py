@@ -36,21 +36,36 @@ def up_to_date() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a and link libkestrel_gpu.so.  Files named *_fast.cu hold the
+    contracted-arithmetic kernels and are the only ones compiled with -fmad=true."""
     if not force and up_to_date():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [NVCC, "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
-           "-I", os.path.join(HERE, "..", "include"), "-o", LIB] + sources()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    common = [NVCC, "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-I", os.path.join(HERE, "..", "include")]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        common += ["-Xptxas", "-v"]
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        fmad = "-fmad=true" if src.endswith("_fast.cu") else "-fmad=false"
+        procs.append((src, subprocess.Popen(common + [fmad, "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = ""
+    for src, pr in procs:
+        out, _ = pr.communicate()
+        log += out
+        if pr.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    r = subprocess.run([NVCC, "-ccbin", HOSTCXX, "-shared", "-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("link failed")
     if verbose:
-        print(r.stderr)
+        print(log)
     return LIB
 
 

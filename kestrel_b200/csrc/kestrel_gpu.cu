@@ -24,6 +24,12 @@
 
 using namespace kgpu;
 
+namespace kgpu {
+// contracted-arithmetic instantiations live in kestrel_stage_fast.cu (compiled with -fmad=true)
+void launch_stage_fast(bool oneD, bool hasBt, bool mm2, int nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a);
+void stage_fast_set_attributes();
+}  // namespace kgpu
+
 #define CUDA_TRY(h, call)                                                                         \
    do {                                                                                           \
       cudaError_t e_ = (call);                                                                    \
@@ -263,12 +269,13 @@ template <bool ONED, bool HASBT, int LIM>
 static void launchStageK(kgpu_handle *h, const StageArgs &a, int nblocks) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM><<<nblocks, NTHREADS, G::smemBytes(), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(), h->stream>>>(h->D, a);
 }
 template <bool ONED>
 static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
    if (nblocks <= 0) return;
    const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
+   if (h->P.arithmetic == 1) { launch_stage_fast(ONED, h->morpho, mm2, nblocks, h->stream, h->D, a); h->launches++; return; }
    if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, true, -1>(h, a, nblocks); }
    else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, false, -1>(h, a, nblocks); }
    h->launches++;
@@ -278,8 +285,8 @@ static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
 static int computeTopo(kgpu_handle *h, int kbt) {
    if (h->nBlocks == 0) return 0;
    const double *btv = h->morpho ? h->btv[kbt] : nullptr;
-   if (h->oneD) topo_planes_kernel<BX1, BY1, true><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList);
-   else topo_planes_kernel<BX2, BY2, false><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList);
+   if (h->oneD) topo_planes_kernel<BX1, BY1, true><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList, h->P.arithmetic == 1 ? 1 : 0);
+   else topo_planes_kernel<BX2, BY2, false><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->b0v, btv, h->topo, h->d_blockList, h->P.arithmetic == 1 ? 1 : 0);
    h->launches++;
    h->topoBtIdx = kbt;
    CUDA_TRY(h, cudaGetLastError());
@@ -795,15 +802,16 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    // opt in to > 48 KB dynamic shared memory for the stage kernel
    {
       int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes();
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, KGPU_LIM_MINMOD2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
    }
+   stage_fast_set_attributes();
    // topography planes (bt planes only when the bed moves)
    {
       double **pl[15] = {&h->topo.b0c, &h->topo.bxc, &h->topo.byc, &h->topo.gamc, &h->topo.xb0, &h->topo.xB, &h->topo.xtan, &h->topo.xgam,
