@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "kgpu_comm.cuh"
 #include "kgpu_hydro.cuh"
 #include "kgpu_morpho.cuh"
@@ -88,6 +90,7 @@ struct kgpu_handle {
    double *EBt = nullptr, *EmD = nullptr;
    double *mx[11] = {};
    TopoPlanes topo = {};       // precomputed cell / face topography for the stage kernel
+   TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
 
@@ -269,7 +272,7 @@ template <bool ONED, bool HASBT, int LIM>
 static void launchStageK(kgpu_handle *h, const StageArgs &a, int nblocks) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(HASBT), h->stream>>>(h->D, a);
 }
 template <bool ONED>
 static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
@@ -279,6 +282,48 @@ static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
    if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, true, -1>(h, a, nblocks); }
    else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, false, -1>(h, a, nblocks); }
    h->launches++;
+}
+
+// Tensor maps for the TMA staging of the stage kernel: every plane is a (rows x pitch) fp64
+// matrix; the box is the halo'd CTA tile (cells), BY face rows (x faces) or BY + 3 rows (y faces).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool buildTensorMaps(kgpu_handle *h) {
+   static EncodeTiledFn encode = nullptr;
+   if (!encode) {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+      encode = (EncodeTiledFn)fn;
+   }
+   const int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
+   const cuuint32_t RX = BX + 4, RY = h->oneD ? 1 : BY + 4, FY = h->oneD ? 1 : BY + 3;
+   std::vector<TmaDesc> maps(TMA_NSLOTS);
+   std::memset(maps.data(), 0, sizeof(TmaDesc) * maps.size());
+   static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap is 128 bytes");
+   auto put = [&](int slot, double *base, cuuint32_t boxRows) {
+      if (!base) return true;
+      CUtensorMap m;
+      cuuint64_t dims[2] = {(cuuint64_t)h->pitch, (cuuint64_t)h->rows};
+      cuuint64_t strides[1] = {(cuuint64_t)h->pitch * sizeof(double)};
+      cuuint32_t box[2] = {RX, boxRows}, estr[2] = {1, 1};
+      if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+         return false;
+      std::memcpy(&maps[slot], &m, sizeof(m));
+      return true;
+   };
+   bool ok = true;
+   for (int k = 0; k < h->nStates; k++) for (int d = 0; d < 4; d++) ok = ok && put(TMA_STATE0 + 4 * k + d, h->S[k][d], RY);
+   ok = ok && put(TMA_B0C, h->topo.b0c, RY) && put(TMA_GAMC, h->topo.gamc, RY) && put(TMA_BTC, h->topo.btc, RY);
+   ok = ok && put(TMA_XB0, h->topo.xb0, BY) && put(TMA_XTAN, h->topo.xtan, BY) && put(TMA_XGAM, h->topo.xgam, BY) &&
+        put(TMA_XB, h->topo.xB, BY) && put(TMA_XBT, h->topo.xbt, BY);
+   ok = ok && put(TMA_YB0, h->topo.yb0, FY) && put(TMA_YTAN, h->topo.ytan, FY) && put(TMA_YGAM, h->topo.ygam, FY) &&
+        put(TMA_YB, h->topo.yB, FY) && put(TMA_YBT, h->topo.ybt, FY);
+   if (!ok) return false;
+   if (cudaMalloc(&h->d_maps, sizeof(TmaDesc) * maps.size()) != cudaSuccess) return false;
+   return cudaMemcpy(h->d_maps, maps.data(), sizeof(TmaDesc) * maps.size(), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
 // (Re)compute the topography planes from the vertex arrays for every listed block.
@@ -305,6 +350,7 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
    }
    a.Iout = h->I0;
    a.T = h->topo;
+   a.maps = h->d_maps; a.mapIn = TMA_STATE0 + 4 * kin;
    if (h->topoBtIdx != kbt) { int rct = computeTopo(h, kbt); if (rct) return rct; }
    a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
    a.ctrl = h->d_ctrl; a.sources = h->d_sources;
@@ -667,7 +713,7 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
-   cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist);
+   cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
    {
       double *pl[15] = {h->topo.b0c, h->topo.bxc, h->topo.byc, h->topo.gamc, h->topo.xb0, h->topo.xB, h->topo.xtan, h->topo.xgam,
@@ -801,7 +847,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    }
    // opt in to > 48 KB dynamic shared memory for the stage kernel
    {
-      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes();
+      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(true), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes(true);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
@@ -819,6 +865,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       int npl = h->morpho ? 15 : 12;
       for (int k = 0; k < npl; k++) if (!allocField(pl[k], 0.0)) return fail("topography planes");
    }
+   if (!buildTensorMaps(h)) return fail("tensor maps (cuTensorMapEncodeTiled)");
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;
    return KGPU_OK;
