@@ -785,6 +785,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    std::memset(&D, 0, sizeof(D));
    D.NX = h->NX; D.NY = h->NY; D.nX = h->nX; D.nY = h->nY; D.nXt = h->nXt; D.nYt = h->nYt;
    D.gtx0 = h->gtx0; D.gty0 = h->gty0; D.gnXt = h->gnXt; D.gnYt = h->gnYt;
+   D.mm2HalfTheta = 0.5 * 1.3;
    D.pitch = h->pitch; D.rows = h->rows;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
    D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;

@@ -56,6 +56,7 @@ struct DevParams {
    double EdBetastar, EdKappa, EdGamma, SwitchRate, SwitchValue;
    double EroRate, EroRateGranular, CriticalShields, EroDepth, EroCritH, BedPorosity, maxPack, SolidDiameter, ws0, nsettling, nu;
    double Hneps, cfl, diffusiveTimeScale, maxdt;
+   double mm2HalfTheta;  // 0.5 * 1.3: MinMod2 half-slope factor of the contracted variant (constant-bank operand)
 };
 
 // Device-resident control block: dt selection and rollback flags never leave the GPU

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Dynamic instruction counts per source line: ncu SASS page zipped with nvdisasm -g line info.
+
+usage: ncu_lines.py <report.ncu-rep> <cubin of the same build> <mangled-kernel-substring> [cells] [top]
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+rep, cubin, pat = sys.argv[1:4]
+cells = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+top = int(sys.argv[5]) if len(sys.argv) > 5 else 60
+
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+lines = out.splitlines()
+start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
+rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+
+txt = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
+on = False
+cur = None
+stack = None
+info = []
+for l in txt:
+    m = re.match(r"\s+\.global\s+(\S+)", l)
+    if m:
+        on = pat in m.group(1)
+        continue
+    if not on:
+        continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
+    if m:
+        cur = (m.group(1).split("/")[-1], int(m.group(2)))
+        stack = (m.group(3).split("/")[-1], int(m.group(4))) if m.group(3) else None
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(@!?U?P\w+\s+)?([A-Z0-9_.]+)", l)
+    if m:
+        info.append((cur, stack, m.group(2).split(".")[0]))
+print("ncu rows", len(rows), "nvdisasm instrs", len(info))
+n = min(len(rows), len(info))
+byline = collections.Counter()
+byouter = collections.Counter()
+ops = collections.defaultdict(collections.Counter)
+stalls = collections.Counter()
+tot = 0
+mism = 0
+for r, (cur, stack, op) in zip(rows[:n], info[:n]):
+    toks = r["Source"].split()
+    rop = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+    if rop != op:
+        mism += 1
+    k = int(r["Instructions Executed"] or 0)
+    tot += k
+    byline[cur] += k
+    ops[cur][op] += k
+    stalls[cur] += int(r["# Samples"] or 0)
+    byouter[stack or cur] += k
+print("opcode mismatches", mism, " total warp instr", tot, f"= {tot / cells:.2f} per cell")
+ts = sum(stalls.values())
+print("--- by innermost line")
+for k, v in byline.most_common(top):
+    print(f"{k[0]}:{k[1]:<5d} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%  stall {100.0 * stalls[k] / max(ts, 1):5.1f}%  {dict((o, round(c / cells, 2)) for o, c in ops[k].most_common(5))}")
+print("--- by call-site line (one level of inlining)")
+for k, v in byouter.most_common(top):
+    print(f"{k[0]}:{k[1]:<5d} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%")
