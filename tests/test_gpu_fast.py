@@ -29,6 +29,23 @@ def test_fast_dambreak(oracle_lib, gpu_lib, ntiles, per, kw):
         assert rel_linf(qg[d], qo[d]) <= TOL, (name, rel_linf(qg[d], qo[d]))
 
 
+def test_fast_dambreak_partial_solids(oracle_lib, gpu_lib):
+    """Solids only in the upper cube: CTA tiles of pure water take the no-solids face loop, the
+    others the general one, and fronts between them move during the run."""
+    rs = dambreak_runset(2, 64)
+    rs.cubes[1].psi = 0.2
+    q4, b0v = dambreak_state(rs)
+    assert (q4[3] == 0).any() and (q4[3] > 0).any()
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    rs.arithmetic = 1
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io, ig = so.integrate_to(1e9, 60), sg.integrate_to(1e9, 60)
+    assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
+    qo, qg = so.download_domain(), sg.download_domain()
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert rel_linf(qg[d], qo[d]) <= TOL, (name, rel_linf(qg[d], qo[d]))
+
+
 def test_fast_lake_at_rest(gpu_lib):
     path = os.path.join(INPUTS, "case_lake_at_rest_hydro_2d.txt")
     sg = run_input(gpu_lib, path, arithmetic=1)
