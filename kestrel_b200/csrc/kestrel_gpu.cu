@@ -351,6 +351,7 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
    a.Iout = h->I0;
    a.T = h->topo;
    a.maps = h->d_maps; a.mapIn = TMA_STATE0 + 4 * kin;
+   a.mx = h->mp(); a.doMaxima = (mode == MODE_FINAL && kq0 == h->i0) ? 1 : 0;
    if (h->topoBtIdx != kbt) { int rct = computeTopo(h, kbt); if (rct) return rct; }
    a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
    a.ctrl = h->d_ctrl; a.sources = h->d_sources;
@@ -607,7 +608,8 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    if ((rc = launchStage(h, MODE_FINAL, ka, kb, kq0, kbt))) return rc;
    h->launches += 2;
    // maxima on the state at the start of the whole step (tileContainer), stamped t + dt (quirk Q1)
-   if (h->nBlocks) {
+   // (fused into the final stage launch when that launch's q0 is the step-start state)
+   if (h->nBlocks && kq0 != h->i0) {
       const double *btm = h->morpho ? h->btv[h->bt0] : nullptr;
       if (h->oneD)
          maxima_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,

@@ -429,4 +429,24 @@ __device__ inline void fluxSources(const DevParams &P, const DevSource *src, dou
    psiQt = 0.0 + sp;
 }
 
+// ---- running maxima (UpdateMaximumHeights/Speeds/Erosion/Deposit/SolidsFraction,
+// TimeStepper.f90:1155-1303): value plane + time-of-maximum plane per field, first-inundation time.
+// Planes are only touched where they can change: bt == 0 on a static bed, and psimax >= 0
+// always (zero-initialised running maximum), so psi == 0 never updates it.
+struct MaximaPtrs {
+   double *Hnmax, *HnmaxT, *umax, *umaxT, *emax, *emaxT, *dmax, *dmaxT, *psimax, *psimaxT, *tfirst;
+};
+__device__ __forceinline__ void updateMaxima(const DevParams &P, const MaximaPtrs &M, size_t g, double tt, double Hn, double spd,
+                                             double bt, double psi) {
+   const bool wet = Hn > P.Hneps;
+   if (wet) {
+      if (M.tfirst[g] == -1) M.tfirst[g] = tt;
+      if (Hn > M.Hnmax[g]) { M.Hnmax[g] = Hn; M.HnmaxT[g] = tt; }
+      if (spd > M.umax[g]) { M.umax[g] = spd; M.umaxT[g] = tt; }
+      if (psi > 0.0) { if (psi > M.psimax[g]) { M.psimax[g] = psi; M.psimaxT[g] = tt; } }
+   }
+   if (bt < 0) { if (-bt > M.emax[g]) { M.emax[g] = -bt; M.emaxT[g] = tt; } }
+   if (bt > 0) { if (bt > M.dmax[g]) { M.dmax[g] = bt; M.dmaxT[g] = tt; } }
+}
+
 }  // namespace kgpu

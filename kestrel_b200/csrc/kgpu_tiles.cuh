@@ -95,9 +95,6 @@ __global__ void tile_flags_kernel(const DevParams P, StatePtrs S0, const double 
 
 // Running maxima (TimeStepper.f90:1155-1303), evaluated on the state at the START of the
 // step and stamped with its END time (quirk Q1, TimeStepper.f90:519-524).
-struct MaximaPtrs {
-   double *Hnmax, *HnmaxT, *umax, *umaxT, *emax, *emaxT, *dmax, *dmaxT, *psimax, *psimaxT, *tfirst;
-};
 template <int BX, int BY>
 __global__ void __launch_bounds__(256) maxima_kernel(const DevParams P, StatePtrs S0, const double *b0v, const double *btv,
                                                         MaximaPtrs M, const uint8_t *tileMask, const int2 *blockList,
@@ -117,15 +114,7 @@ __global__ void __launch_bounds__(256) maxima_kernel(const DevParams P, StatePtr
    q.w = S0.q[QW][g]; q.hu = S0.q[QHU][g]; q.hv = S0.q[QHV][g]; q.hpsi = S0.q[QHPSI][g];
    centreTopoGlobal(P, b0v, btv, ci, cj, q.b0, q.bt, q.bx, q.by);
    desingularise(P, q, true);
-   if (q.Hn > P.Hneps) {
-      if (M.tfirst[g] == -1) M.tfirst[g] = tt;
-      if (q.Hn > M.Hnmax[g]) { M.Hnmax[g] = q.Hn; M.HnmaxT[g] = tt; }
-   }
-   double spd = sqrt(speed2(P, q.u, q.v, q.bx, q.by));
-   if (spd > M.umax[g] && q.Hn > P.Hneps) { M.umax[g] = spd; M.umaxT[g] = tt; }
-   if (q.bt < 0) { if (-q.bt > M.emax[g]) { M.emax[g] = -q.bt; M.emaxT[g] = tt; } }
-   if (q.bt > 0) { if (q.bt > M.dmax[g]) { M.dmax[g] = q.bt; M.dmaxT[g] = tt; } }
-   if (q.Hn > P.Hneps) { if (q.psi > M.psimax[g]) { M.psimax[g] = q.psi; M.psimaxT[g] = tt; } }
+   updateMaxima(P, M, g, tt, q.Hn, sqrt(speed2(P, q.u, q.v, q.bx, q.by)), q.bt, q.psi);
 }
 
 // ---- host transfer staging: one tile <-> one contiguous staging buffer
