@@ -96,13 +96,13 @@ def oracle_library():
     return capi.Library(path, "kor_")
 
 
-def cpu_baseline(steps: int, warmup: int, size: int = CPU_SAMPLE_SIZE, threads: int = 0):
+def cpu_baseline(steps: int, warmup: int, size: int = CPU_SAMPLE_SIZE, threads: int = 0, morpho: bool = False):
     """The oracle on the host cores, bounded sample of the same workload."""
     from kestrel_b200 import capi
     from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state
     lib = oracle_library()
     cores = threads or os.cpu_count() or 1
-    rs = dambreak_runset(size // 128, 128)
+    rs = dambreak_runset(size // 128, 128, morpho=morpho)
     q4, b0v = dambreak_state(rs)
     p, keep = rs.to_c()
     st = capi.Stepper(lib, p, keep)
@@ -159,6 +159,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--arithmetic", type=int, default=1,
                     help="1 (default) contracted fp64, held to the north-star 1e-10 against the oracle; 0 faithful (bit-identical to the oracle)")
+    ap.add_argument("--workload", default="hydro", choices=["hydro", "morpho"],
+                    help="hydro: the headline dam-break (Chezy, erosion off); morpho: SURVEY 8(d)'s second run (Variable drag, "
+                         "Mixed erosion, psi = 0.1), one step = one Strang step H(dt) M(2dt) H(dt)")
     ap.add_argument("--no-faithful", action="store_true", help="skip the side measurement of the faithful-arithmetic variant")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -182,15 +185,19 @@ def main():
 
     size = args.size or 16384
     free_b, total_b = torch.cuda.mem_get_info()
-    need = 30 * (size + 64) ** 2 * 8
+    morpho = args.workload == "morpho"
+    planes = 64 if morpho else 44   # device planes of one handle + staging
+    need = planes * (size + 64) ** 2 * 8
     while need > 0.9 * free_b and size > 1024:
         size //= 2
-        need = 30 * (size + 64) ** 2 * 8
+        need = planes * (size + 64) ** 2 * 8
     # weak scaling: every GPU owns a size x size block of a (px*size) x (py*size) periodic domain
     px, py = decomposition(world)
     T = size // 128
-    rs = dambreak_runset(T, 128)
+    rs = dambreak_runset(T, 128, morpho=morpho)
     if world > 1:
+        if morpho:
+            raise SystemExit("the morphodynamic operator is single-device this round (DESIGN.md section 4)")
         rs.nXtiles, rs.nYtiles = px * T, py * T
         rs.Ytilesize = None
         rs.finalize()
@@ -270,8 +277,8 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "hydro_stage_kernel", "kernel_ms": k_ms, "kernel_launches_timed": int(rl.value),
-                "kernel_share_of_step": 4 * k_ms / (ms / args.steps), "peak_source": peak_src,
-                "step_frac_of_hbm_roofline": cells * ALG_BYTES_PER_CELL_UPDATE / (ms / args.steps * 1e-3) / 1e9 / peak}
+                "kernel_share_of_step": (8 if morpho else 4) * k_ms / (ms / args.steps), "peak_source": peak_src,
+                "step_frac_of_hbm_roofline": cells * (1120 if morpho else ALG_BYTES_PER_CELL_UPDATE) / (ms / args.steps * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the C-ABI with host buffers
     e2e = None
@@ -328,8 +335,8 @@ def main():
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cb = cpu_baseline(steps=6, warmup=1)
-        serial = cpu_baseline(steps=2, warmup=1, threads=1)
+        cb = cpu_baseline(steps=6, warmup=1, morpho=morpho)
+        serial = cpu_baseline(steps=2, warmup=1, threads=1, morpho=morpho)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cb["serial_value"] = serial["value"]  # the Fortran reference is single-threaded
 
@@ -337,8 +344,11 @@ def main():
         line = {"metric": "cell-updates/s (fp64)", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off, all tiles active "
-                                       "(BASELINE.json configs[4])",
+                "config": {"workload": ("synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off, all tiles active "
+                                        "(BASELINE.json configs[4])") if not morpho else
+                                       ("synthetic dam-break with morphodynamics (SURVEY 8d second run): Variable drag, Mixed erosion, "
+                                        "Spearman-Manning deposition, psi0 = 0.1; one step = one Strang step H(dt) M(2dt) H(dt) = 8 stage "
+                                        "launches + 3 morphodynamic stages; 1120 algorithmic B per cell-update"),
                            "cells_per_gpu": cells, "grid": f"{rs.NX}x{rs.NY}", "tiles": f"{rs.nXtiles}x{rs.nYtiles} of 128x128",
                            "decomposition": f"{px}x{py} blocks, 2-cell halos by ncclSend/ncclRecv overlapped with the interior, "
                                             "one ncclAllReduce(min) per dt decision" if world > 1 else "single device",

@@ -69,5 +69,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOSTSRC = os.path.join(HERE, "host_cpp")
+HOSTBIN = os.path.join(HERE, "bin", "kestrel_gpu_run")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ host driver above the C-ABI (kestrel_b200/host_cpp): g++ only, links libkestrel_gpu.so
+    through an $ORIGIN-relative rpath so the in-tree binary runs wherever the snapshot lands."""
+    srcs = [os.path.join(HOSTSRC, f) for f in sorted(os.listdir(HOSTSRC)) if f.endswith(".cpp")]
+    dep = [os.path.join(HOSTSRC, f) for f in os.listdir(HOSTSRC)] + [os.path.join(HERE, "..", "include", "kestrel_gpu.h"), LIB]
+    if not force and os.path.exists(HOSTBIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOSTBIN) for d in dep):
+        return HOSTBIN
+    os.makedirs(os.path.dirname(HOSTBIN), exist_ok=True)
+    cmd = [HOSTCXX, "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-I", os.path.join(HERE, "..", "include"), "-I", HOSTSRC] + srcs + \
+          ["-L", LIBDIR, "-lkestrel_gpu", "-Wl,-rpath,$ORIGIN/../lib", "-o", HOSTBIN]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("host driver build failed")
+    return HOSTBIN
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))
