@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -91,6 +92,7 @@ struct kgpu_handle {
    double *mx[11] = {};
    TopoPlanes topo = {};       // precomputed cell / face topography for the stage kernel
    TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
+   int prefetchDistance = 0;   // L2 prefetch distance of the stage kernel in CTAs (one resident wave)
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
 
@@ -352,6 +354,7 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
    a.T = h->topo;
    a.maps = h->d_maps; a.mapIn = TMA_STATE0 + 4 * kin;
    a.mx = h->mp(); a.doMaxima = (mode == MODE_FINAL && kq0 == h->i0) ? 1 : 0;
+   a.prefetchDistance = h->prefetchDistance;
    if (h->topoBtIdx != kbt) { int rct = computeTopo(h, kbt); if (rct) return rct; }
    a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
    a.ctrl = h->d_ctrl; a.sources = h->d_sources;
@@ -869,6 +872,13 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       for (int k = 0; k < npl; k++) if (!allocField(pl[k], 0.0)) return fail("topography planes");
    }
    if (!buildTensorMaps(h)) return fail("tensor maps (cuTensorMapEncodeTiled)");
+   {
+      cudaDeviceProp prop;
+      int nsm = 148;
+      if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) nsm = prop.multiProcessorCount;
+      h->prefetchDistance = 3 * nsm;
+      if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
+   }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;
    return KGPU_OK;
