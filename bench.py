@@ -191,6 +191,19 @@ def main():
     while need > 0.9 * free_b and size > 1024:
         size //= 2
         need = planes * (size + 64) ** 2 * 8
+    # host side: every rank pins q4 + out (2 x 32 B/cell) and builds the state with numpy temporaries
+    # (~110 B/cell in all); all ranks share one box's RAM, so shrink rather than swap or get killed
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        while world * 110 * size * size > 0.7 * avail and size > 1024:
+            size //= 2
+    except ImportError:
+        pass
+    if world > 1:  # every rank must agree on the block size
+        tsz = torch.tensor([size], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tsz, op=dist.ReduceOp.MIN)
+        size = int(tsz.item())
     # weak scaling: every GPU owns a size x size block of a (px*size) x (py*size) periodic domain
     px, py = decomposition(world)
     T = size // 128

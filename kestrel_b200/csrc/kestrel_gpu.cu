@@ -274,7 +274,7 @@ template <bool ONED, bool HASBT, int LIM>
 static void launchStageK(kgpu_handle *h, const StageArgs &a, int nblocks) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(HASBT), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
 }
 template <bool ONED>
 static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
@@ -853,7 +853,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    }
    // opt in to > 48 KB dynamic shared memory for the stage kernel
    {
-      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(true), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes(true);
+      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(true, false), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes(true, false);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
       cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);

@@ -14,7 +14,7 @@ template <bool ONED, bool HASBT, int LIM>
 static void launchFastK(int nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
    constexpr int BX = ONED ? FBX1 : FBX2, BY = ONED ? FBY1 : FBY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true><<<nblocks, 256, G::smemBytes(HASBT), s>>>(P, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true><<<nblocks, 256, G::smemBytes(HASBT, true), s>>>(P, a);
 }
 
 void launch_stage_fast(bool oneD, bool hasBt, bool mm2, int nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
@@ -28,7 +28,7 @@ void launch_stage_fast(bool oneD, bool hasBt, bool mm2, int nblocks, cudaStream_
 }
 
 void stage_fast_set_attributes() {
-   int s2 = (int)StageGeom<FBX2, FBY2, false>::smemBytes(true), s1 = (int)StageGeom<FBX1, FBY1, true>::smemBytes(true);
+   int s2 = (int)StageGeom<FBX2, FBY2, false>::smemBytes(true, true), s1 = (int)StageGeom<FBX1, FBY1, true>::smemBytes(true, true);
    cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, false, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
    cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, false, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
    cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, true, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);

@@ -19,10 +19,11 @@ lines = out.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
 
-txt = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
+txt = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.splitlines()
 on = False
-cur = None
-stack = None
+cur = None     # innermost source line of the instruction
+outer = None   # line of the kernel body it was inlined into (end of the "inlined at" chain)
+chain = False
 info = []
 for l in txt:
     m = re.match(r"\s+\.global\s+(\S+)", l)
@@ -31,18 +32,23 @@ for l in txt:
         continue
     if not on:
         continue
-    m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', l)
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
-        cur = (m.group(1).split("/")[-1], int(m.group(2)))
-        stack = (m.group(3).split("/")[-1], int(m.group(4))) if m.group(3) else None
+        here = (m.group(1).split("/")[-1], int(m.group(2)))
+        if not chain:
+            cur = here
+        outer = here
+        chain = True
         continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(@!?U?P\w+\s+)?([A-Z0-9_.]+)", l)
     if m:
-        info.append((cur, stack, m.group(2).split(".")[0]))
+        info.append((cur, outer, m.group(2).split(".")[0]))
+    chain = False
 print("ncu rows", len(rows), "nvdisasm instrs", len(info))
 n = min(len(rows), len(info))
 byline = collections.Counter()
 byouter = collections.Counter()
+opsouter = collections.defaultdict(collections.Counter)
 ops = collections.defaultdict(collections.Counter)
 stalls = collections.Counter()
 tot = 0
@@ -58,11 +64,26 @@ for r, (cur, stack, op) in zip(rows[:n], info[:n]):
     ops[cur][op] += k
     stalls[cur] += int(r["# Samples"] or 0)
     byouter[stack or cur] += k
+    opsouter[stack or cur][op] += k
 print("opcode mismatches", mism, " total warp instr", tot, f"= {tot / cells:.2f} per cell")
 ts = sum(stalls.values())
 print("--- by innermost line")
 for k, v in byline.most_common(top):
     print(f"{k[0]}:{k[1]:<5d} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%  stall {100.0 * stalls[k] / max(ts, 1):5.1f}%  {dict((o, round(c / cells, 2)) for o, c in ops[k].most_common(5))}")
-print("--- by call-site line (one level of inlining)")
+print("--- by line of the kernel body (inlined callees attributed to their call site)")
 for k, v in byouter.most_common(top):
-    print(f"{k[0]}:{k[1]:<5d} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%")
+    print(f"{k[0]}:{k[1]:<5d} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%  {dict((o, round(c / cells, 2)) for o, c in opsouter[k].most_common(5))}")
+import os
+rng = os.environ.get("PHASES")  # e.g. "283:stage,312:A,343:C,515:D,652:cfl,678:end"
+if rng:
+    marks = [(int(a), b) for a, b in (x.split(":") for x in rng.split(","))]
+    agg = collections.Counter()
+    for (f, ln), v in byouter.items():
+        name = "pre"
+        for a, b in marks:
+            if ln >= a:
+                name = b
+        agg[name] += v
+    print("--- by phase")
+    for k, v in agg.most_common():
+        print(f"{k:8s} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%")
