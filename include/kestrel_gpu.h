@@ -227,6 +227,12 @@ int kgpu_rhs_timing(kgpu_handle *h, double *ms, int64_t *launches, int32_t reset
 void *kgpu_stream(kgpu_handle *h);
 const char *kgpu_version(void);
 
+/* Diagnostics: ONE evaluation of CalculateHydraulicRHS (src/HydraulicRHS.f90:64-137) on the
+   current state, without advancing it: ddtExplicit E4[(4, NY, NX)], ddtImplicit I[(NY, NX)]
+   (either may be NULL) and the advised time step of ComputeAdvisedTimeStep (:141-176) for
+   `substep`.  Used by the parity tests to compare a single RHS with the oracle's. */
+int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, double *dt);
+
 #ifdef __cplusplus
 }
 #endif
