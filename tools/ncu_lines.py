@@ -78,12 +78,14 @@ rng = os.environ.get("PHASES")  # e.g. "283:stage,312:A,343:C,515:D,652:cfl,678:
 if rng:
     marks = [(int(a), b) for a, b in (x.split(":") for x in rng.split(","))]
     agg = collections.Counter()
+    aggops = collections.defaultdict(collections.Counter)
     for (f, ln), v in byouter.items():
         name = "pre"
         for a, b in marks:
             if ln >= a:
                 name = b
         agg[name] += v
+        aggops[name].update(opsouter[(f, ln)])
     print("--- by phase")
     for k, v in agg.most_common():
-        print(f"{k:8s} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%")
+        print(f"{k:8s} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%  {dict((o, round(c / cells, 2)) for o, c in aggops[k].most_common(14))}")
