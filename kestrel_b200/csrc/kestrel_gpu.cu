@@ -793,6 +793,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    D.mm2HalfTheta = 0.5 * 1.3;
    D.pitch = h->pitch; D.rows = h->rows;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
+   D.bcDirichlet = p->bcs == KGPU_BC_DIRICHLET ? 1 : 0; D.bcU = p->bcsuval; D.bcV = p->bcsvval; D.bcPsi = p->bcspsival;
    D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;
    D.eroTrans = p->erosion_transition; D.damp = p->morpho_damp; D.fswitch = p->fswitch;
    D.nSources = p->n_sources;

@@ -56,6 +56,8 @@ struct DevParams {
    double EdBetastar, EdKappa, EdGamma, SwitchRate, SwitchValue;
    double EroRate, EroRateGranular, CriticalShields, EroDepth, EroCritH, BedPorosity, maxPack, SolidDiameter, ws0, nsettling, nu;
    double Hneps, cfl, diffusiveTimeScale, maxdt;
+   int bcDirichlet;      // ghost cells of domain-edge tiles carry the boundary values (UpdateTiles.f90:571-664)
+   double bcU, bcV, bcPsi;
    double mm2HalfTheta;  // 0.5 * 1.3: MinMod2 half-slope factor of the contracted variant (constant-bank operand)
 };
 
