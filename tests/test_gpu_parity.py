@@ -240,3 +240,87 @@ def test_open_boundary_conditions(oracle_lib, gpu_lib, bcs, oned):
             assert exact, f"{bcs} {name}: {err}"
     # the boundary did something: the run differs from the initial mass
     assert abs(sg.volume_rows[-1][1] - sg.volume_rows[0][1]) > 0
+
+
+_CLOSURE_MATRIX = (
+    [dict(erosion=e) for e in ("simple", "fluid", "granular", "mixed")] +
+    [dict(deposition=d) for d in ("none", "simple", "spearman manning")] +
+    [dict(erosion_transition=t) for t in ("smooth", "step", "off")] +
+    [dict(morpho_damp=m) for m in ("none", "tanh", "rat3")] +
+    [dict(drag="variable", fswitch=f) for f in ("tanh", "rat3", "cos", "linear", "equal", "off", "one", "step")]
+)
+
+
+@pytest.mark.parametrize("kw", _CLOSURE_MATRIX, ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items()).replace(" ", "_"))
+def test_morpho_closure_matrix(oracle_lib, gpu_lib, kw):
+    """Every runtime-selectable erosion / deposition / transition / damping / switch closure
+    (Closures.f90:320-356, 566-915), one at a time, on the morphodynamic dam-break: fields and bed to
+    1e-10, identical step and rollback counts."""
+    rs = dambreak_runset(2, 32, morpho=True, **kw)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io, ig = so.integrate_to(1e9, 10), sg.integrate_to(1e9, 10)
+    assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
+    assert abs(io.t - ig.t) <= 1e-12 * io.t
+    (qo, bo), (qg, bg) = so.download_domain(True), sg.download_domain(True)
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert rel_linf(qg[d], qo[d]) <= MORPHO_TOL, (kw, name, rel_linf(qg[d], qo[d]))
+    if np.max(np.abs(bo)) > 0:
+        assert rel_linf(bg, bo) <= MORPHO_TOL, kw
+    so.close(); sg.close()
+
+
+def test_flux_source_time_series_and_restart(oracle_lib, gpu_lib):
+    """Two flux sources with multi-entry time series (Equations.f90:456-618: linear interpolation in
+    time, source switching off), t start != 0, a max dt cap -- and a restart: stopping, downloading
+    every tile (maxima and tfirst included), uploading into a fresh handle and continuing must equal
+    the uninterrupted run bit for bit (the reference's restart identity, tests/netcdf_restart.sh)."""
+    from kestrel_b200.host.settings import FluxSource, RunSet
+    from kestrel_b200.host.run import Simulation
+
+    def make():
+        rs = RunSet(nXtiles=9, nYtiles=9, nXpertile=12, nYpertile=12, Xtilesize=12.0, bcs="halt", drag="chezy", ChezyCo=0.02,
+                    erosion="off", topog_func="xyslope", topog_params=[-0.08, 0.03], tstart=2.0, tend=8.0, Nout=2, TileBuffer=2,
+                    maxdt=0.05, EddyViscosity=0.01)
+        rs.sources = [FluxSource(x=-3.0, y=2.0, radius=3.0, time=[0.0, 3.0, 5.0, 6.0], flux=[2.0, 6.0, 1.0, 0.0], psi=[0.0, 0.1, 0.2, 0.0]),
+                      FluxSource(x=8.0, y=-5.0, radius=2.0, time=[0.0, 10.0], flux=[1.5, 1.5], psi=[0.05, 0.05])]
+        return rs.finalize()
+
+    so = Simulation(make(), oracle_lib).run()
+    sg = Simulation(make(), gpu_lib).run()
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert [i.nsteps for i in sg.infos] == [i.nsteps for i in so.infos]
+    for a, b in zip(sg.snapshots[1:], so.snapshots[1:]):
+        for name, (err, exact) in compare_snapshots(a, b).items():
+            assert exact, f"{name}: {err}"
+    for k in sg.snapshots[-1]:
+        assert np.array_equal(sg.snapshots[-1][k]["maxima"], so.snapshots[-1][k]["maxima"])
+        assert np.array_equal(sg.snapshots[-1][k]["tfirst"], so.snapshots[-1][k]["tfirst"])
+
+    # restart at the first output time
+    rs = make()
+    first = Simulation(rs, gpu_lib)
+    t1 = rs.tstart + rs.DeltaT
+    first.stepper.integrate_to(t1)
+    tiles = first.download_active()
+    rs2 = make()
+    rs2.tstart = t1
+    rs2.finalize()
+    from kestrel_b200.host.topog import make_heights_callback
+    from kestrel_b200.host.sources import load_source_conditions
+    load_source_conditions(rs2)  # NumCellsInSrc of the sources
+    p, keep = rs2.to_c(make_heights_callback(rs2))
+    from kestrel_b200 import capi
+    st = capi.Stepper(gpu_lib, p, keep)
+    src_tiles = {tid for tid, T in load_source_conditions(make()).items() if T.contains_source}
+    for tid in sorted(tiles):
+        T = tiles[tid]
+        st.upload_tile(tid, T["u"], b0v=np.ascontiguousarray(T["b0"]), maxima=T["maxima"], tfirst=T["tfirst"],
+                       contains_source=tid in src_tiles)
+    st.integrate_to(rs.tend)
+    resumed = {int(t): st.download_tile(int(t)) for t in st.active_tiles()}
+    for name, (err, exact) in compare_snapshots(resumed, sg.snapshots[-1]).items():
+        assert exact, f"restart {name}: {err}"
+    for k in resumed:
+        assert np.array_equal(resumed[k]["maxima"], sg.snapshots[-1][k]["maxima"])
