@@ -288,7 +288,21 @@ def main():
             traffic = per_cell * cells
     except Exception:
         pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    # second roofline: the fp64 pipe issues one warp instruction per 2 cycles per SM sub-partition;
+    # fp64 warp-instructions per cell come from the committed ncu capture, the launch time is live
+    fp64 = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            per = json.load(fh)["fp64_pipe_warp_instructions_per_cell_per_launch"]["contracted" if args.arithmetic == 1 else "faithful"]
+        props = torch.cuda.get_device_properties(local_rank)
+        mhz = clocks.get("sm_mhz") or 1965.0
+        pk = props.multi_processor_count * 4 * 0.5 * mhz * 1e6
+        ach = per * cells / (k_ms * 1e-3)
+        fp64 = {"achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": pk, "frac": ach / pk, "warp_inst_per_cell": per,
+                "note": "the pipe that binds first for this scheme (DESIGN.md section 5); peak = SMs x 4 x 0.5 per cycle at the sampled SM clock"}
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "fp64_pipe": fp64,
                 "kernel": "hydro_stage_kernel", "kernel_ms": k_ms, "kernel_launches_timed": int(rl.value),
                 "kernel_share_of_step": (8 if morpho else 4) * k_ms / (ms / args.steps), "peak_source": peak_src,
                 "step_frac_of_hbm_roofline": cells * (1120 if morpho else ALG_BYTES_PER_CELL_UPDATE) / (ms / args.steps * 1e-3) / 1e9 / peak}
