@@ -84,6 +84,8 @@ struct kgpu_handle {
    int ic = 3, id = 4;         // morphodynamics: state after M, second H result
    bool e0Valid = false;       // E0/I0 hold the substep-1 RHS of S[i0]
    double *Um = nullptr, *Vm = nullptr;  // velocities frozen over M
+   double *mc[2][4] = {};      // morphodynamic stages: centre bt, bx, by and clamped Hn of the stage (ping-pong)
+   double *mcHn0 = nullptr;    // clamped Hn of the state M starts from
    double *E0[4] = {}, *I0 = nullptr;
    double *b0v = nullptr;
    double *btv[4] = {};        // morphodynamics: bed change at vertices for q0 and the three stages
@@ -713,7 +715,8 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaSetDevice(h->dev);
    if (h->stream) cudaStreamSynchronize(h->stream);
    for (int k = 0; k < 5; k++) for (int d = 0; d < 4; d++) cudaFree(h->S[k][d]);
-   cudaFree(h->Um); cudaFree(h->Vm);
+   cudaFree(h->Um); cudaFree(h->Vm); cudaFree(h->mcHn0);
+   for (int a = 0; a < 2; a++) for (int b = 0; b < 4; b++) cudaFree(h->mc[a][b]);
    for (int d = 0; d < 4; d++) { cudaFree(h->E0[d]); cudaFree(h->btv[d]); }
    cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
@@ -828,6 +831,8 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    if (h->morpho) {
       for (int d = 0; d < 4; d++) if (!allocField(&h->btv[d], 0.0)) return fail("btv");
       if (!allocField(&h->EmD, 0.0) || !allocField(&h->Um, 0.0) || !allocField(&h->Vm, 0.0)) return fail("EmD");
+      for (int a = 0; a < 2; a++) for (int b = 0; b < 4; b++) if (!allocField(&h->mc[a][b], 0.0)) return fail("morphodynamic centre planes");
+      if (!allocField(&h->mcHn0, 0.0)) return fail("morphodynamic centre planes");
    }
    for (int k = 0; k < 10; k++) if (!allocField(&h->mx[k], 0.0)) return fail("maxima");
    if (!allocField(&h->mx[10], -1.0)) return fail("tfirst");

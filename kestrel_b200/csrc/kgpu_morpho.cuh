@@ -35,6 +35,13 @@ struct MorphoArgs {
    int allActive;
    double a0, a1;               // RK weights: bt_new = a0*bt0 + a1*(btk + dt*rhs); a0 = 0 selects stage 1
    double dtMorpho;
+   // cell-centred planes of the stage bed btk (bt, bx, by at centres and the clamped Hn of the stage
+   // state), written once per cell by the previous stage's cell kernel (stage 1: the hydraulic
+   // topography planes + morpho_prepare) instead of being re-derived from the vertices by every reader
+   const double *b0c;                   // static
+   const double *cBt, *cBx, *cBy, *cHn; // of (btk, stage state)
+   const double *zBt, *zBx, *zBy, *zGam; // of bt0 (= the hydraulic topography planes during M)
+   double *nBt, *nBx, *nBy, *nHn;       // of (btn, state being written)
 };
 
 __device__ __forceinline__ bool cellTileActive(const DevParams &P, const uint8_t *mask, int allActive, int ci, int cj) {
@@ -55,8 +62,9 @@ __device__ __forceinline__ double storedHn(const DevParams &P, const double *w, 
 // velocities of the hydraulic result as its 4th RHS evaluation left them (pre-correction momenta)
 template <int BX, int BY>
 __global__ void __launch_bounds__(256) morpho_prepare_kernel(const DevParams P, const double *w, const double *hpsi, const double *huPre,
-                                                                const double *hvPre, const double *b0v, const double *btv, double *U,
-                                                                double *V, const uint8_t *tileMask, const int2 *blockList, int allActive) {
+                                                                const double *hvPre, const double *b0c, const double *btc,
+                                                                const double *bxc, const double *byc, double *U, double *V, double *HnOut,
+                                                                const uint8_t *tileMask, const int2 *blockList, int allActive) {
    if (threadIdx.x >= BX * BY) return;
    const int2 bo = blockList[blockIdx.x];
    int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
@@ -65,9 +73,10 @@ __global__ void __launch_bounds__(256) morpho_prepare_kernel(const DevParams P, 
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    CellState q;
    q.w = w[g]; q.hpsi = hpsi[g]; q.hu = huPre[g]; q.hv = hvPre[g];
-   centreTopoGlobal(P, b0v, btv, ci, cj, q.b0, q.bt, q.bx, q.by);
+   q.b0 = b0c[g]; q.bt = btc[g]; q.bx = bxc[g]; q.by = byc[g];   // centre topography of bt0 (hydraulic planes)
    desingularise(P, q, true);
    U[g] = q.u; V[g] = q.v;
+   HnOut[g] = q.Hn;   // clamped at zero: the stored u(Hn) the dry test of the first stage reads
 }
 
 // CalculateMorphodynamicRHS, cell part (MorphodynamicRHS.f90:96-145)
@@ -81,12 +90,17 @@ __global__ void __launch_bounds__(256) morpho_emd_kernel(const DevParams P, cons
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    CellState q;
    q.w = A.w[g]; q.hpsi = A.hpsi[g]; q.hu = 0.0; q.hv = 0.0;
-   centreTopoGlobal(P, A.b0v, A.btk, ci, cj, q.b0, q.bt, q.bx, q.by);
+   q.b0 = A.b0c[g]; q.bt = A.cBt[g]; q.bx = A.cBx[g]; q.by = A.cBy[g];
    desingularise(P, q, false);
    q.u = A.U[g]; q.v = A.V[g];
    double eps = P.Hneps;
-   bool dry = q.Hn < eps || storedHn(P, A.w, A.b0v, A.btk, ci - 1, cj) < eps || storedHn(P, A.w, A.b0v, A.btk, ci + 1, cj) < eps;
-   if (!P.oneD) dry = dry || storedHn(P, A.w, A.b0v, A.btk, ci, cj - 1) < eps || storedHn(P, A.w, A.b0v, A.btk, ci, cj + 1) < eps;
+   // neighbours: the plane inside active tiles (their halo images included), the vertices elsewhere
+   auto nbHn = [&](int i, int j) -> double {
+      if (cellTileActive(P, A.tileMask, A.allActive, i, j)) return A.cHn[(size_t)(j + YO) * P.pitch + (i + XO)];
+      return storedHn(P, A.w, A.b0v, A.btk, i, j);
+   };
+   bool dry = q.Hn < eps || nbHn(ci - 1, cj) < eps || nbHn(ci + 1, cj) < eps;
+   if (!P.oneD) dry = dry || nbHn(ci, cj - 1) < eps || nbHn(ci, cj + 1) < eps;
    A.EmD[g] = dry ? 0.0 : erosionMinusDeposition(P, q);
 }
 
@@ -114,12 +128,23 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
       if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
       return A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
    };
+   // centre slopes of a cell next to the vertex: the stage's plane inside active tiles (halo images
+   // included), the vertex arrays elsewhere
+   auto slopes = [&](int i, int j, double &bx_, double &by_) {
+      if (cellTileActive(P, A.tileMask, A.allActive, i, j)) {
+         size_t gc = (size_t)(j + YO) * P.pitch + (i + XO);
+         bx_ = A.cBx[gc]; by_ = A.cBy[gc];
+      } else {
+         double b0c_, btc_;
+         centreTopoGlobal(P, A.b0v, A.btk, i, j, b0c_, btc_, bx_, by_);
+      }
+   };
    if (!P.oneD) {
-      double b0c, btc, bx[4], by[4];
-      centreTopoGlobal(P, A.b0v, A.btk, vi - 1, vj - 1, b0c, btc, bx[0], by[0]);
-      centreTopoGlobal(P, A.b0v, A.btk, vi - 1, vj, b0c, btc, bx[1], by[1]);
-      centreTopoGlobal(P, A.b0v, A.btk, vi, vj - 1, b0c, btc, bx[2], by[2]);
-      centreTopoGlobal(P, A.b0v, A.btk, vi, vj, b0c, btc, bx[3], by[3]);
+      double bx[4], by[4];
+      slopes(vi - 1, vj - 1, bx[0], by[0]);
+      slopes(vi - 1, vj, bx[1], by[1]);
+      slopes(vi, vj - 1, bx[2], by[2]);
+      slopes(vi, vj, bx[3], by[3]);
       double dbdx = 0.25 * kahan4(bx[0], bx[1], bx[2], bx[3]);
       double dbdy = 0.25 * kahan4(by[0], by[1], by[2], by[3]);
       double gam = gamma2(P, dbdx, dbdy);
@@ -127,9 +152,9 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
    } else {
       bool lAct = (P.periodic || vi - 1 >= 0) && cellTileActive(P, A.tileMask, A.allActive, vi - 1, 0);
       bool rAct = (P.periodic || vi < P.NX) && cellTileActive(P, A.tileMask, A.allActive, vi, 0);
-      double b0c, btc, bxl = 0.0, bxr = 0.0, byd;
-      if (lAct) centreTopoGlobal(P, A.b0v, A.btk, vi - 1, 0, b0c, btc, bxl, byd);
-      if (rAct) centreTopoGlobal(P, A.b0v, A.btk, vi, 0, b0c, btc, bxr, byd);
+      double bxl = 0.0, bxr = 0.0, byd;
+      if (lAct) slopes(vi - 1, 0, bxl, byd);
+      if (rAct) slopes(vi, 0, bxr, byd);
       if (lAct && rAct) {
          double dbdx = 0.5 * (bxl + bxr);
          double gam = gamma2(P, dbdx, 0.0);
@@ -155,10 +180,10 @@ __global__ void __launch_bounds__(256) morpho_cell_kernel(const DevParams P, con
    if (ci >= P.NX || cj >= P.NY) return;
    if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) return;
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
-   double b0c, bt0c, bx0, by0, btnc, bxn, byn;
-   centreTopoGlobal(P, A.b0v, A.bt0, ci, cj, b0c, bt0c, bx0, by0);
+   double b0c, btnc, bxn, byn;
+   const double bt0c = A.zBt[g];                       // centre planes of bt0
    centreTopoGlobal(P, A.b0v, A.btn, ci, cj, b0c, btnc, bxn, byn);
-   double gamold = gamma2(P, bx0, by0), gamnew = gamma2(P, bxn, byn);
+   double gamold = A.zGam[g], gamnew = gamma2(P, bxn, byn);
    double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
    double db = btnc - bt0c;
    double w = -db / gamnew / gamnew;
@@ -169,11 +194,17 @@ __global__ void __launch_bounds__(256) morpho_cell_kernel(const DevParams P, con
    double Hnpsi = -(1.0 - P.BedPorosity) * db / gamnew;
    Hnpsi = Hnpsi + A.hpsi0[g] * gamold / gamnew;
    A.hpsin[g] = Hnpsi;
+   // centre planes of the new bed and the clamped depth of the new state, for the next stage's readers
+   A.nBt[g] = btnc; A.nBx[g] = bxn; A.nBy[g] = byn;
+   double Hn_new = computeHn(w, b0c, btnc, gamnew);
+   A.nHn[g] = Hn_new < 0.0 ? 0.0 : Hn_new;
 }
 
 struct CheckArgs {
    const double *w0, *hpsi0, *w3;
    const double *b0v, *bt0, *bt3;
+   const double *b0c, *zBt, *zGam;        // centre planes of bt0 (hydraulic topography planes)
+   const double *c3Bt, *c3Bx, *c3By;      // centre planes of bt3 (written by the third stage's cell kernel)
    const uint8_t *tileMask;
    const int2 *blockList;
    Ctrl *ctrl;
@@ -199,10 +230,8 @@ __global__ void __launch_bounds__(256) morpho_check_kernel(const DevParams P, co
    if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) return;
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    const double EPS = 2.220446049250313e-16;
-   double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
-   centreTopoGlobal(P, A.b0v, A.bt0, ci, cj, b0c, bt0c, bx0, by0);
-   centreTopoGlobal(P, A.b0v, A.bt3, ci, cj, b0c, bt3c, bx3, by3);
-   double gamold = gamma2(P, bx0, by0), gamnew = gamma2(P, bx3, by3);
+   const double b0c = A.b0c[g], bt0c = A.zBt[g], bt3c = A.c3Bt[g];
+   double gamold = A.zGam[g], gamnew = gamma2(P, A.c3Bx[g], A.c3By[g]);
    double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
    double Hn_new = computeHn(A.w3[g], b0c, bt3c, gamnew);
    double deltaBt = bt3c - bt0c;

@@ -37,8 +37,8 @@ static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    int rc = fillHaloPlanes(h, pl, 1, true);
    if (rc) return rc;
    morpho_cell_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
-   double *pc[2] = {a.wn, a.hpsin};
-   rc = fillHaloPlanes(h, pc, 2, false);
+   double *pc[5] = {a.wn, a.hpsin, a.nBx, a.nBy, a.nHn};   // the next stage reads slopes and depths of halo cells
+   rc = fillHaloPlanes(h, pc, 5, false);
    h->launches += 3;
    CUDA_TRY(h, cudaGetLastError());
    return rc;
@@ -46,34 +46,45 @@ static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
 
 static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &again) {
    again = false;
-   int rc;
+   int rc = 0;
    const int R1 = h->ib, PRE = h->ia, MA = h->ic, MB = h->id;
    const int allAct = h->allActive() ? 1 : 0;
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
    if (h->nBlocks == 0) return 0;
    // (the halo of the H1 result was produced together with it)
    // velocities frozen over M = those of H1's 4th RHS evaluation (pre-correction momenta)
+   // the hydraulic topography planes are those of bt0 here (H1 just ran with them)
+   if (h->topoBtIdx != h->bt0 && (rc = computeTopo(h, h->bt0))) return rc;
    if (h->oneD)
       morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
-                                                                            h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
+                                                                            h->topo.b0c, h->topo.btc, h->topo.bxc, h->topo.byc, h->Um, h->Vm,
+                                                                            h->mcHn0, h->d_tileMask, h->d_blockList, allAct);
    else
       morpho_prepare_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
-                                                                            h->b0v, h->btv[h->bt0], h->Um, h->Vm, h->d_tileMask, h->d_blockList, allAct);
+                                                                            h->topo.b0c, h->topo.btc, h->topo.bxc, h->topo.byc, h->Um, h->Vm,
+                                                                            h->mcHn0, h->d_tileMask, h->d_blockList, allAct);
+   { double *ph[1] = {h->mcHn0}; if ((rc = fillHaloPlanes(h, ph, 1, false))) return rc; }
    h->launches++;
    double dt_morpho = 2.0 * dt_hydro;
    MorphoArgs a;
    a.w0 = h->S[R1][QW]; a.hpsi0 = h->S[R1][QHPSI]; a.U = h->Um; a.V = h->Vm; a.b0v = h->b0v; a.bt0 = h->btv[h->bt0];
    a.EmD = h->EmD; a.tileMask = h->d_tileMask; a.blockList = h->d_blockList; a.ctrl = h->d_ctrl; a.allActive = allAct;
    a.dtMorpho = dt_morpho;
+   a.b0c = h->topo.b0c; a.zBt = h->topo.btc; a.zBx = h->topo.bxc; a.zBy = h->topo.byc; a.zGam = h->topo.gamc;
+   auto centreIn = [&](const double *bt, const double *bx, const double *by, const double *hn) { a.cBt = bt; a.cBx = bx; a.cBy = by; a.cHn = hn; };
+   auto centreOut = [&](int set) { a.nBt = h->mc[set][0]; a.nBx = h->mc[set][1]; a.nBy = h->mc[set][2]; a.nHn = h->mc[set][3]; };
    // stage 1 (TimeStepper.f90:566-610)
+   centreIn(h->topo.btc, h->topo.bxc, h->topo.byc, h->mcHn0); centreOut(0);
    a.w = h->S[R1][QW]; a.hpsi = h->S[R1][QHPSI]; a.btk = h->btv[h->bt0]; a.btn = h->btv[h->bt1];
    a.wn = h->S[MA][QW]; a.hpsin = h->S[MA][QHPSI]; a.a0 = 0.0; a.a1 = 1.0;
    if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
    // stage 2 (:612-655)
+   centreIn(h->mc[0][0], h->mc[0][1], h->mc[0][2], h->mc[0][3]); centreOut(1);
    a.w = h->S[MA][QW]; a.hpsi = h->S[MA][QHPSI]; a.btk = h->btv[h->bt1]; a.btn = h->btv[h->bt2];
    a.wn = h->S[MB][QW]; a.hpsin = h->S[MB][QHPSI]; a.a0 = 0.75; a.a1 = 0.25;
    if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
    // stage 3 (:657-699)
+   centreIn(h->mc[1][0], h->mc[1][1], h->mc[1][2], h->mc[1][3]); centreOut(0);
    a.w = h->S[MB][QW]; a.hpsi = h->S[MB][QHPSI]; a.btk = h->btv[h->bt2]; a.btn = h->btv[h->bt3];
    a.wn = h->S[MA][QW]; a.hpsin = h->S[MA][QHPSI]; a.a0 = 1.0 / 3.0; a.a1 = 2.0 / 3.0;
    if ((rc = h->oneD ? morphoStageT<true>(h, a) : morphoStageT<false>(h, a))) return rc;
@@ -81,6 +92,7 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    ctrl_morpho_reset_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl);
    CheckArgs c;
    c.w0 = h->S[R1][QW]; c.hpsi0 = h->S[R1][QHPSI]; c.w3 = h->S[MA][QW]; c.b0v = h->b0v; c.bt0 = h->btv[h->bt0]; c.bt3 = h->btv[h->bt3];
+   c.b0c = h->topo.b0c; c.zBt = h->topo.btc; c.zGam = h->topo.gamc; c.c3Bt = h->mc[0][0]; c.c3Bx = h->mc[0][1]; c.c3By = h->mc[0][2];
    c.tileMask = h->d_tileMask; c.blockList = h->d_blockList; c.ctrl = h->d_ctrl; c.list = h->d_redist; c.listCap = h->redistCap; c.allActive = allAct;
    if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
