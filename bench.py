@@ -209,8 +209,6 @@ def main():
     T = size // 128
     rs = dambreak_runset(T, 128, morpho=morpho)
     if world > 1:
-        if morpho:
-            raise SystemExit("the morphodynamic operator is single-device this round (DESIGN.md section 4)")
         rs.nXtiles, rs.nYtiles = px * T, py * T
         rs.Ytilesize = None
         rs.finalize()

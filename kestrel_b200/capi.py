@@ -17,6 +17,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 GPU_LIB_PATH = os.path.join(_HERE, "lib", "libkestrel_gpu.so")
+if os.environ.get("KGPU_LIB"):  # tuning experiments: another build of the same sources (tools/build_variant.py)
+    GPU_LIB_PATH = os.environ["KGPU_LIB"]
 
 # status codes (include/kestrel_gpu.h)
 KGPU_OK, KGPU_ERR_ARG, KGPU_ERR_CUDA, KGPU_ERR_HALT_BC, KGPU_ERR_DT, KGPU_ERR_UNSUPPORTED = range(6)

@@ -29,7 +29,7 @@ using namespace kgpu;
 
 namespace kgpu {
 // contracted-arithmetic instantiations live in kestrel_stage_fast.cu (compiled with -fmad=true)
-void launch_stage_fast(bool oneD, bool hasBt, bool mm2, int nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a);
+void launch_stage_fast(bool oneD, bool hasBt, bool mm2, dim3 grid, cudaStream_t s, const DevParams &P, const StageArgs &a);
 void stage_fast_set_attributes();
 }  // namespace kgpu
 
@@ -95,6 +95,8 @@ struct kgpu_handle {
    TopoPlanes topo = {};       // precomputed cell / face topography for the stage kernel
    TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
    int prefetchDistance = 0;   // L2 prefetch distance of the stage kernel in CTAs (one resident wave)
+   int tune = 0;               // StageArgs::tune bits; bit 3 here: 2-D grid without the block list when every block is listed
+   int nbxAll = 0, nbyAll = 0; // CTA tiles per row / column of the local domain
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
 
@@ -208,6 +210,7 @@ static int refreshMasks(kgpu_handle *h) {
    CUDA_TRY(h, cudaMemcpyAsync(h->d_tileSource, srcm.data(), srcm.size(), cudaMemcpyHostToDevice, h->stream));
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
    int nbx = (h->NX + BX - 1) / BX, nby = (h->NY + BY - 1) / BY;
+   h->nbxAll = nbx; h->nbyAll = nby;
    std::vector<int2> list;
    list.reserve((size_t)nbx * nby);
    for (int by = 0; by < nby; by++)
@@ -273,18 +276,27 @@ static int fillHaloVertices(kgpu_handle *h, double *v) {
 }
 
 template <bool ONED, bool HASBT, int LIM>
-static void launchStageK(kgpu_handle *h, const StageArgs &a, int nblocks) {
+static void launchStageK(kgpu_handle *h, const StageArgs &a, dim3 grid) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<nblocks, NTHREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<grid, NTHREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
 }
+// nblocks CTAs taken from a.blockList, or -- when the list is the whole local domain in row-major order --
+// a 2-D grid whose block indices are the tile coordinates (no dependent load before the TMA issue)
 template <bool ONED>
-static void launchStageT(kgpu_handle *h, const StageArgs &a, int nblocks) {
+static void launchStageT(kgpu_handle *h, StageArgs a, int nblocks) {
    if (nblocks <= 0) return;
+   dim3 grid(nblocks);
+   a.directNbx = 0;
+   a.tune = h->tune & ~8;
+   if ((h->tune & 8) && a.blockList == h->d_blockList && nblocks == h->nbxAll * h->nbyAll && h->nbyAll <= 65535) {
+      a.directNbx = h->nbxAll;
+      grid = dim3(h->nbxAll, h->nbyAll);
+   }
    const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
-   if (h->P.arithmetic == 1) { launch_stage_fast(ONED, h->morpho, mm2, nblocks, h->stream, h->D, a); h->launches++; return; }
-   if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, true, -1>(h, a, nblocks); }
-   else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, nblocks); else launchStageK<ONED, false, -1>(h, a, nblocks); }
+   if (h->P.arithmetic == 1) { launch_stage_fast(ONED, h->morpho, mm2, grid, h->stream, h->D, a); h->launches++; return; }
+   if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, grid); else launchStageK<ONED, true, -1>(h, a, grid); }
+   else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, grid); else launchStageK<ONED, false, -1>(h, a, grid); }
    h->launches++;
 }
 
@@ -769,9 +781,8 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       c.size = p->comm_size; c.rank = p->comm_rank; c.px = p->comm_px; c.py = p->comm_py;
       bool okc = c.px >= 1 && c.py >= 1 && c.px * c.py == c.size && c.rank >= 0 && c.rank < c.size &&
                  p->nXtiles % c.px == 0 && p->nYtiles % c.py == 0 && !(h->oneD && c.py != 1);
-      if (!okc || h->morpho || !h->globalPeriodic) {
-         fprintf(stderr, "kgpu_create: decomposition needs px*py = size, tiles divisible by px, py, periodic bcs and the "
-                         "hydraulic operator only (round 1)\n");
+      if (!okc || !h->globalPeriodic) {
+         fprintf(stderr, "kgpu_create: decomposition needs px*py = size, tiles divisible by px, py and periodic bcs\n");
          delete h;
          return okc ? KGPU_ERR_UNSUPPORTED : KGPU_ERR_ARG;
       }
@@ -795,6 +806,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    D.gtx0 = h->gtx0; D.gty0 = h->gty0; D.gnXt = h->gnXt; D.gnYt = h->gnYt;
    D.mm2HalfTheta = 0.5 * 1.3;
    D.pitch = h->pitch; D.rows = h->rows;
+   D.haloValid = (p->comm_size > 1 && h->globalPeriodic) ? 1 : 0;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
    D.bcDirichlet = p->bcs == KGPU_BC_DIRICHLET ? 1 : 0; D.bcU = p->bcsuval; D.bcV = p->bcsvval; D.bcPsi = p->bcspsival;
    D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;
@@ -884,6 +896,8 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) nsm = prop.multiProcessorCount;
       h->prefetchDistance = 3 * nsm;
       if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
+      h->tune = 15;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0; all four +5.5 %
+      if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)
    }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;
@@ -1082,7 +1096,7 @@ int kgpu_comm_attach(kgpu_handle *h, const void *id_in) {
    ncclComm_t comm;
    NCCL_TRY(h, g_nccl.CommInitRank(&comm, h->comm.size, id, h->comm.rank));
    h->comm.nccl = comm;
-   size_t nx = (size_t)4 * (h->NY + 1) * 2, ny = (size_t)4 * (h->NX + 5) * 2;
+   size_t nx = (size_t)8 * (h->NY + 1) * 2, ny = (size_t)8 * (h->NX + 5) * 2;   // up to 8 fields per exchange
    for (int k = 0; k < 4; k++) {
       size_t n = (k < 2 ? nx : ny) * sizeof(double);
       CUDA_TRY(h, cudaMalloc(&h->comm.sendBuf[k], n));

@@ -7,7 +7,7 @@
 namespace kgpu {
 
 struct StripArgs {
-   double *f[4];
+   double *f[8];
    int nf;
 };
 

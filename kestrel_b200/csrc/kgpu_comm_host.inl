@@ -124,3 +124,13 @@ static int allreduceCfl(kgpu_handle *h, int slot) {
    NCCL_TRY(h, g_nccl.AllReduce(p, p, 1, ncclDouble, ncclMin, (ncclComm_t)h->comm.nccl, h->stream));
    return 0;
 }
+
+// the morphodynamic refine flag and the length of the redistribution list (adjacent ints of the control
+// block): every rank must take the same decision (TimeStepper.f90:709-773), so reduce with max
+static int allreduceMorphoFlags(kgpu_handle *h) {
+   if (!h->comm.active) return 0;
+   static_assert(offsetof(Ctrl, nRedist) == offsetof(Ctrl, refineMorpho) + sizeof(int), "flags must be adjacent");
+   int *p = &h->d_ctrl->refineMorpho;
+   NCCL_TRY(h, g_nccl.AllReduce(p, p, 2, ncclInt, ncclMax, (ncclComm_t)h->comm.nccl, h->stream));
+   return 0;
+}

@@ -48,6 +48,7 @@ struct DevParams {
    int pitch;             // doubles per padded row
    int rows;              // padded rows
    int oneD, periodic, geom, morpho;
+   int haloValid;   // decomposed periodic run: cells / vertices beyond the local block are images owned by another rank (or the local wrap)
    int limiter, drag, erosion, deposition, eroTrans, damp, fswitch;
    int nSources;
    double dx, dy, dxR, dyR, xSize, ySize;

@@ -111,12 +111,15 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
    int nvy = P.oneD ? 1 : P.NY + 1;
    if (vi > P.NX || vj >= nvy) return;
    if (P.periodic && (vi == P.NX || (!P.oneD && vj == P.NY))) return;  // aliases, refreshed by the halo fill
+   // decomposed run: cells beyond the block are images held in the halo (E - D included, exchanged by the
+   // host after the cell kernel); the seam vertices are then computed identically by both ranks
+   const bool wrapOrHalo = P.periodic || P.haloValid;
    // vertex of an active tile?
    bool any = false;
    for (int dj = (P.oneD ? 0 : -1); dj <= 0; dj++)
       for (int di = -1; di <= 0; di++) {
          int i = vi + di, j = vj + dj;
-         if (!P.periodic && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) continue;
+         if (!wrapOrHalo && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) continue;
          if (cellTileActive(P, A.tileMask, A.allActive, i, j)) any = true;
       }
    if (!any) return;
@@ -124,7 +127,7 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
    double psib = 1.0 - P.BedPorosity;
    double rhs;
    auto emd = [&](int i, int j) -> double {
-      if (!P.periodic && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) return 0.0;
+      if (!wrapOrHalo && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) return 0.0;
       if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
       return A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
    };
@@ -150,8 +153,8 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
       double gam = gamma2(P, dbdx, dbdy);
       rhs = -0.25 * gam / psib * kahan4(emd(vi - 1, vj - 1), emd(vi - 1, vj), emd(vi, vj - 1), emd(vi, vj));
    } else {
-      bool lAct = (P.periodic || vi - 1 >= 0) && cellTileActive(P, A.tileMask, A.allActive, vi - 1, 0);
-      bool rAct = (P.periodic || vi < P.NX) && cellTileActive(P, A.tileMask, A.allActive, vi, 0);
+      bool lAct = (wrapOrHalo || vi - 1 >= 0) && cellTileActive(P, A.tileMask, A.allActive, vi - 1, 0);
+      bool rAct = (wrapOrHalo || vi < P.NX) && cellTileActive(P, A.tileMask, A.allActive, vi, 0);
       double bxl = 0.0, bxr = 0.0, byd;
       if (lAct) slopes(vi - 1, 0, bxl, byd);
       if (rAct) slopes(vi, 0, bxr, byd);

@@ -11,6 +11,7 @@ __global__ void ctrl_morpho_reset_kernel(Ctrl *c) {
 }
 
 static int fillHaloPlanes(kgpu_handle *h, double *const *planes, int n, bool vertices) {
+   if (h->comm.active) return exchangeHalo(h, planes, n, vertices, h->stream);   // n <= 8 (StripArgs)
    if (!h->periodic) return 0;
    HaloArgs a;
    a.nf = n;
@@ -31,6 +32,11 @@ template <bool ONED>
 static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
+   if (h->comm.active) {   // the bed kernel reads E - D of the cells across the block edge (single device: by wrapped index)
+      double *pe[1] = {a.EmD};
+      int rce = exchangeHalo(h, pe, 1, false, h->stream);
+      if (rce) return rce;
+   }
    dim3 gv((h->NX + 1 + 127) / 128, h->oneD ? 1 : h->NY + 1);
    morpho_bed_kernel<<<gv, 128, 0, h->stream>>>(h->D, a);
    double *pl[1] = {a.btn};
@@ -97,9 +103,16 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    h->launches += 2;
+   if ((rc = allreduceMorphoFlags(h))) return rc;
    if ((rc = readCtrl(h))) return rc;
    bool refine = h->h_ctrl->refineMorpho != 0;
    int nRed = h->h_ctrl->nRedist;
+   if (!refine && nRed > 0 && h->comm.active) {
+      // RedistributeGrid walks ONE list sorted over the whole domain and every correction feeds the next
+      // (Redistribute.f90:203-247): a chain may cross any number of blocks.  Not decomposed yet.
+      h->err = "excess deposition must be redistributed (Redistribute.f90:203): not supported in decomposed runs yet";
+      return KGPU_ERR_UNSUPPORTED;
+   }
    if (!refine && nRed > h->redistCap) refine = true;  // list overflow: treat like a failed redistribution
    if (!refine && nRed > 0) {
       // sorted ascending by excess, ties in scan order: active-tile order, then j, then i (Redistribute.f90:69-101)

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=4)
     ap.add_argument("--per", type=int, default=64)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--morpho", action="store_true", help="Strang-split run with the morphodynamic operator (bed included in the comparison)")
+    ap.add_argument("--arithmetic", type=int, default=0)
     args = ap.parse_args()
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lrank)
@@ -44,8 +46,9 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     lib = capi.load_gpu()
     px, py = decomposition(world)
-    rs = dambreak_runset(args.tiles, args.per)
+    rs = dambreak_runset(args.tiles, args.per, morpho=args.morpho)
     rs.device = lrank
+    rs.arithmetic = args.arithmetic
     rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
     blk = rank_block(rs, rank, px, py)
     q4, b0v = dambreak_state(rs, blk)
@@ -54,31 +57,41 @@ def main():
     attach(lib, st, rank, dev)
     st.upload_domain(q4, b0v)
     info = st.integrate_to(1e30, args.steps)
-    q = st.download_domain()
+    q, bt = st.download_domain(want_bt=True)
     # gather blocks on rank 0
     t = torch.from_numpy(q).to(dev)
     parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
     dist.gather(t, parts, 0)
+    tb = torch.from_numpy(np.ascontiguousarray(bt)).to(dev)
+    bparts = [torch.empty_like(tb) for _ in range(world)] if rank == 0 else None
+    dist.gather(tb, bparts, 0)
     ok = True
     if rank == 0:
-        rs1 = dambreak_runset(args.tiles, args.per)
+        rs1 = dambreak_runset(args.tiles, args.per, morpho=args.morpho)
         rs1.device = lrank
+        rs1.arithmetic = args.arithmetic
         Q4, B0 = dambreak_state(rs1)
         p1, k1 = rs1.to_c()
         s1 = capi.Stepper(lib, p1, k1)
         s1.upload_domain(Q4, B0)
         i1 = s1.integrate_to(1e30, args.steps)
-        ref = s1.download_domain()
+        ref, refbt = s1.download_domain(want_bt=True)
         got = np.empty_like(ref)
+        gotbt = np.empty_like(refbt)
         for r in range(world):
             tx0, ty0, ntx, nty = rank_block(rs1, r, px, py)
             got[:, ty0 * args.per:(ty0 + nty) * args.per, tx0 * args.per:(tx0 + ntx) * args.per] = parts[r].cpu().numpy()
+            # seam vertices are held by both neighbours (and must agree): later blocks overwrite with equal values
+            gotbt[ty0 * args.per:(ty0 + nty) * args.per + 1, tx0 * args.per:(tx0 + ntx) * args.per + 1] = bparts[r].cpu().numpy()
         same_t = (i1.t == info.t and i1.nsteps == info.nsteps and i1.nrefines == info.nrefines)
         exact = [bool(np.array_equal(got[d], ref[d])) for d in range(4)]
         err = [float(np.max(np.abs(got[d] - ref[d]))) for d in range(4)]
-        ok = same_t and all(exact)
-        print(f"MULTIGPU world={world} decomposition={px}x{py} grid={rs1.NX}x{rs1.NY} steps={info.nsteps} t={info.t!r} "
-              f"same_t={same_t} bitwise={exact} maxabs={err} -> {'PASS' if ok else 'FAIL'}", flush=True)
+        bed_exact = bool(np.array_equal(gotbt, refbt))
+        bed_moved = float(np.max(np.abs(refbt)))
+        ok = same_t and all(exact) and bed_exact and (bed_moved > 0.0 or not args.morpho)
+        print(f"MULTIGPU world={world} decomposition={px}x{py} grid={rs1.NX}x{rs1.NY} morpho={args.morpho} steps={info.nsteps} "
+              f"refines={info.nrefines} t={info.t!r} same_t={same_t} bitwise={exact} maxabs={err} bed_bitwise={bed_exact} "
+              f"max|bt|={bed_moved:.3e} -> {'PASS' if ok else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     st.close()

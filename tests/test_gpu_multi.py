@@ -24,3 +24,17 @@ def test_decomposed_run_is_bitwise_equal(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_decomposed_morphodynamic_run_is_bitwise_equal(world):
+    """Strang-split run H M H across ranks: halo exchange of the stage beds, E - D and the centre planes,
+    max-allreduce of the refine flags; state AND bed must be bitwise equal to the 1-GPU run."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29520 + world), os.path.join(ROOT, "tests", "run_multigpu.py"), "--tiles", "8", "--per", "32", "--steps", "12",
+           "--morpho"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout
