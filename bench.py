@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--workload", default="hydro", choices=["hydro", "morpho"],
                     help="hydro: the headline dam-break (Chezy, erosion off); morpho: SURVEY 8(d)'s second run (Variable drag, "
                          "Mixed erosion, psi = 0.1), one step = one Strang step H(dt) M(2dt) H(dt)")
+    ap.add_argument("--output-intervals", type=int, default=0,
+                    help="extra leg: N output intervals of --steps steps each, blocking kgpu_download_domain against the "
+                         "asynchronous kgpu_output_begin / kgpu_output_wait (SURVEY 8f rank 2)")
     ap.add_argument("--no-faithful", action="store_true", help="skip the side measurement of the faithful-arithmetic variant")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -325,6 +328,28 @@ def main():
         e2e = {"value": cells * world * k_e2e / t1, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / k_e2e,
                "d2h_bytes_per_step": d2h / k_e2e, "interval_steps": k_e2e, "interval_s": t1,
                "note": "one output interval: kgpu_upload_domain + kgpu_integrate_to(K steps) + kgpu_download_domain, pinned host buffers"}
+    # ---- output intervals: blocking download against the asynchronous gather (host buffers pinned in both)
+    pipelined = None
+    if args.output_intervals > 0 and world == 1:
+        n_int, k_int = args.output_intervals, args.steps
+        outs = [out, torch.empty_like(q4).pin_memory()]
+        res = {}
+        for mode in ("blocking", "async"):
+            barrier()
+            t0 = time.perf_counter()
+            for it in range(n_int):
+                st.integrate_to(1e30, k_int)
+                if mode == "blocking":
+                    st.lib.download_domain(st.h, capi._ptr(outs[it % 2].numpy()), None)
+                else:
+                    st.output_begin(outs[it % 2].numpy())   # waits for the previous output, snapshots, returns
+            if mode == "async":
+                st.output_wait()
+            torch.cuda.synchronize()
+            res[mode] = cells * n_int * k_int / (time.perf_counter() - t0)
+        pipelined = {"intervals": n_int, "steps_per_interval": k_int, "unit": "cell-updates/s", "blocking": res["blocking"],
+                     "async": res["async"], "d2h_bytes_per_interval": out.numel() * 8,
+                     "note": "N x (K steps + whole-state output to pinned host memory); async = kgpu_output_begin/kgpu_output_wait"}
     st.close()
 
     # ---- the other arithmetic variant beside the headline (device-resident, fewer steps)
@@ -383,6 +408,8 @@ def main():
                            "rolled_back_attempts": nref},
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "other_arithmetic": other}
+        if pipelined:
+            line["output_intervals"] = pipelined
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

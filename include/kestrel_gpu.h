@@ -201,6 +201,20 @@ int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertic
                        const double *bt_vertices);
 int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices);
 
+/* ---- asynchronous output gather --------------------------
+ * Replaces the blocking read of grid%tileContainer before OutputSolutionData
+ * (src/TimeStepper.f90:106-109, src/Output.f90:170-227) when the host wants to keep
+ * integrating while the output interval is written.  kgpu_output_begin takes a device-side
+ * snapshot of the current state (4 planes, + the bed with morphodynamics; a device copy at HBM
+ * speed) and starts its transfer to the host buffers on a copy stream; it returns at once and
+ * kgpu_integrate_to may be called again immediately.  kgpu_output_wait blocks until the
+ * buffers hold the snapshot.  Same layout as kgpu_download_domain; the buffers should be
+ * page-locked (cudaHostRegister / pinned allocation) for the copy to overlap the time steps,
+ * and must stay valid and untouched until kgpu_output_wait returns.  One output may be in
+ * flight per handle: a second kgpu_output_begin first waits for the previous one.        */
+int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices);
+int kgpu_output_wait(kgpu_handle *h);
+
 /* ---- multi-GPU (one process per GPU; 2-D block decomposition of the tile grid) */
 
 /* Bytes of an opaque communicator id (ncclUniqueId). */

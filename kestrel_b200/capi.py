@@ -136,6 +136,8 @@ class Library:
             ("comm_attach", C.c_int, [C.c_void_p, C.c_void_p]),
             ("comm_block", C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
             ("set_pinned", C.c_int, [C.c_void_p, C.c_int32]),
+            ("output_begin", C.c_int, [C.c_void_p, _dp, _dp]),
+            ("output_wait", C.c_int, [C.c_void_p]),
         ]:
             try:
                 f(name, res, args)
@@ -251,6 +253,15 @@ class Stepper:
         btv = np.zeros(((1 if self.oneD else self.NY + 1), self.NX + 1)) if want_bt else None
         self._check(self.lib.download_domain(self.h, _ptr(q4), _ptr(btv)))
         return (q4, btv) if want_bt else q4
+
+    def output_begin(self, q4: np.ndarray, btv: Optional[np.ndarray] = None):
+        """Asynchronous output gather: device snapshot now, transfer into q4 (and btv) while the next
+        kgpu_integrate_to calls run.  The arrays must stay alive and untouched until output_wait()."""
+        assert q4.size == 4 * self.NX * self.NY
+        self._check(self.lib.output_begin(self.h, _ptr(q4), _ptr(btv)))
+
+    def output_wait(self):
+        self._check(self.lib.output_wait(self.h))
 
     def debug_rhs(self, substep: int = 1):
         E = np.zeros((4, self.NY, self.NX))

@@ -43,8 +43,9 @@ void stage_fast_set_attributes();
    } while (0)
 
 namespace {
-constexpr int BX2 = 32, BY2 = 7;   // 2-D stage tile: 224 cells, 487 faces = 2 passes of 256 threads
-constexpr int NTHREADS = 256;
+constexpr int BX2 = 32, BY2 = KGPU_STAGE_BY2;   // 2-D stage tile: 224 cells, 487 faces = 2 passes of 256 threads
+constexpr int NTHREADS = 256;                   // elementwise kernels over a stage tile
+constexpr int STAGE_THREADS = KGPU_STAGE_THREADS;
 constexpr int BX1 = 128, BY1 = 1;  // 1-D stage tile
 const double HUGE_D = std::numeric_limits<double>::max();
 }  // namespace
@@ -125,6 +126,12 @@ struct kgpu_handle {
    bool timeRhs = false;
    double rhsMs = 0.0;
    int64_t rhsLaunches = 0;
+
+   // asynchronous output gather: device snapshot + copy stream
+   double *snap[5] = {};
+   cudaStream_t copyStream = nullptr;
+   cudaEvent_t evSnap = nullptr, evCopied = nullptr;
+   bool outputPending = false;
 
    bool allActive() const { return (int)activeList.size() == nTiles; }
    StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
@@ -279,7 +286,7 @@ template <bool ONED, bool HASBT, int LIM>
 static void launchStageK(kgpu_handle *h, const StageArgs &a, dim3 grid) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<grid, NTHREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<grid, STAGE_THREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
 }
 // nblocks CTAs taken from a.blockList, or -- when the list is the whole local domain in row-major order --
 // a 2-D grid whose block indices are the tile coordinates (no dependent load before the TMA issue)
@@ -748,6 +755,10 @@ int kgpu_destroy(kgpu_handle *h) {
    if (h->comm.stream) cudaStreamDestroy(h->comm.stream);
    if (h->evA) cudaEventDestroy(h->evA);
    if (h->evB) cudaEventDestroy(h->evB);
+   if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
+   if (h->evSnap) cudaEventDestroy(h->evSnap);
+   if (h->evCopied) cudaEventDestroy(h->evCopied);
+   for (int k = 0; k < 5; k++) cudaFree(h->snap[k]);
    if (h->stream) cudaStreamDestroy(h->stream);
    delete h;
    return 0;
@@ -896,7 +907,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) nsm = prop.multiProcessorCount;
       h->prefetchDistance = 3 * nsm;
       if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
-      h->tune = 15;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0; all four +5.5 %
+      h->tune = 31;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0, bit 4 +2.2 %; all five +7.9 %
       if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)
    }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
@@ -1049,6 +1060,52 @@ int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices) {
       else std::memset(bt_vertices, 0, sizeof(double) * (size_t)(h->NX + 1) * nvy);
    }
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return KGPU_OK;
+}
+
+// Asynchronous output gather: snapshot on the compute stream (device copy), transfer on a copy stream.
+int kgpu_output_wait(kgpu_handle *h) {
+   if (!h) return KGPU_ERR_ARG;
+   if (!h->outputPending) return KGPU_OK;
+   cudaSetDevice(h->dev);
+   CUDA_TRY(h, cudaEventSynchronize(h->evCopied));
+   h->outputPending = false;
+   return KGPU_OK;
+}
+
+int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices) {
+   if (!h || !q4) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   int rc = kgpu_output_wait(h);   // one output in flight: the snapshot planes are about to be rewritten
+   if (rc) return rc;
+   if (!h->copyStream) {
+      CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->evSnap, cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->evCopied, cudaEventDisableTiming | cudaEventBlockingSync));
+   }
+   const bool wantBt = bt_vertices && h->morpho;
+   size_t fb = h->fieldElems * sizeof(double);
+   for (int k = 0; k < (wantBt ? 5 : 4); k++)
+      if (!h->snap[k]) CUDA_TRY(h, cudaMalloc(&h->snap[k], fb));
+   // the state buffer of this step is recycled two steps from now: keep a copy (HBM speed, a few ms at 16384^2)
+   for (int d = 0; d < 4; d++) CUDA_TRY(h, cudaMemcpyAsync(h->snap[d], h->S[h->i0][d], fb, cudaMemcpyDeviceToDevice, h->stream));
+   if (wantBt) CUDA_TRY(h, cudaMemcpyAsync(h->snap[4], h->btv[h->bt0], fb, cudaMemcpyDeviceToDevice, h->stream));
+   CUDA_TRY(h, cudaEventRecord(h->evSnap, h->stream));
+   CUDA_TRY(h, cudaStreamWaitEvent(h->copyStream, h->evSnap, 0));
+   size_t nc = (size_t)h->NX * h->NY;
+   size_t dp = (size_t)h->pitch * sizeof(double);
+   for (int d = 0; d < 4; d++)
+      CUDA_TRY(h, cudaMemcpy2DAsync(q4 + d * nc, (size_t)h->NX * sizeof(double), h->snap[d] + (size_t)YO * h->pitch + XO, dp,
+                                    (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyDeviceToHost, h->copyStream));
+   if (bt_vertices) {
+      int nvy = h->oneD ? 1 : h->NY + 1;
+      if (wantBt)
+         CUDA_TRY(h, cudaMemcpy2DAsync(bt_vertices, (size_t)(h->NX + 1) * sizeof(double), h->snap[4] + (size_t)YO * h->pitch + XO, dp,
+                                       (size_t)(h->NX + 1) * sizeof(double), nvy, cudaMemcpyDeviceToHost, h->copyStream));
+      else std::memset(bt_vertices, 0, sizeof(double) * (size_t)(h->NX + 1) * nvy);
+   }
+   CUDA_TRY(h, cudaEventRecord(h->evCopied, h->copyStream));
+   h->outputPending = true;
    return KGPU_OK;
 }
 

@@ -8,13 +8,13 @@
 
 namespace kgpu {
 
-constexpr int FBX2 = 32, FBY2 = 7, FBX1 = 128, FBY1 = 1;
+constexpr int FBX2 = 32, FBY2 = KGPU_STAGE_BY2, FBX1 = 128, FBY1 = 1;
 
 template <bool ONED, bool HASBT, int LIM>
 static void launchFastK(dim3 nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
    constexpr int BX = ONED ? FBX1 : FBX2, BY = ONED ? FBY1 : FBY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true><<<nblocks, 256, G::smemBytes(HASBT, true), s>>>(P, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true><<<nblocks, KGPU_STAGE_THREADS, G::smemBytes(HASBT, true), s>>>(P, a);
 }
 
 void launch_stage_fast(bool oneD, bool hasBt, bool mm2, dim3 nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {

@@ -28,7 +28,7 @@ for pr in procs:
         sys.exit(log)
     lines = log.splitlines()
     for i, l in enumerate(lines):
-        if "hydro_stage_kernelILi32ELi7ELb0ELb0ELi1E" in l and "Function properties" in l:
+        if "hydro_stage_kernelILi32E" in l and "ELb0ELb0ELi1E" in l and "Function properties" in l:
             print(l.split("_ZN4kgpu18")[1][:60], "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
 lib = os.path.join(out, "libkestrel_gpu.so")
 subprocess.check_call([kb.NVCC, "-ccbin", kb.HOSTCXX, "-shared", "-o", lib] + objs + ["-ldl"])
