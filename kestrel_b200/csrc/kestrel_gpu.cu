@@ -16,6 +16,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda.h>
@@ -59,6 +60,15 @@ struct kgpu_comm {
    double *sendBuf[4] = {}, *recvBuf[4] = {};
    cudaStream_t stream = nullptr;       // communication stream
    cudaEvent_t evBoundary = nullptr, evHalo = nullptr;
+};
+
+// device buffers of the redistribution walk across ranks (kgpu_morpho_host.inl), grown on demand
+struct RedistGlobalBufs {
+   size_t cap = 0;                 // entries (all ranks) the buffers hold
+   RedistEntry *dEntries = nullptr;
+   double *dPatch = nullptr, *dSend = nullptr;
+   int *dCounts = nullptr, *dVslot = nullptr, *dCslot = nullptr, *dVkey = nullptr, *dVbase = nullptr, *dCkey = nullptr, *dCbase = nullptr;
+   int sendCap = 0;
 };
 
 struct kgpu_handle {
@@ -132,6 +142,7 @@ struct kgpu_handle {
    cudaStream_t copyStream = nullptr;
    cudaEvent_t evSnap = nullptr, evCopied = nullptr;
    bool outputPending = false;
+   RedistGlobalBufs rg;
 
    bool allActive() const { return (int)activeList.size() == nTiles; }
    StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
@@ -236,7 +247,12 @@ static int refreshMasks(kgpu_handle *h) {
       // blocks touching the edge of the local domain are computed first so that their strips can travel
       // while the interior is still being computed
       std::vector<int2> bnd, inr;
-      for (const int2 &b : list) ((b.x == 0 || b.x == nbx - 1 || b.y == 0 || b.y == nby - 1) ? bnd : inr).push_back(b);
+      // (every block that holds one of the two outermost cell columns / rows: with NY % BY == 1 the last block row
+      // has a single row of cells and the second-to-last row of the strip lives in the block below it)
+      for (const int2 &b : list) {
+         bool edge = b.x * BX < 2 || (b.x + 1) * BX > h->NX - 2 || (!h->oneD && (b.y * BY < 2 || (b.y + 1) * BY > h->NY - 2));
+         (edge ? bnd : inr).push_back(b);
+      }
       h->nBoundary = (int)bnd.size(); h->nInterior = (int)inr.size();
       if (h->nBoundary) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockBoundary, bnd.data(), bnd.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
       if (h->nInterior) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockInterior, inr.data(), inr.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
@@ -759,6 +775,8 @@ int kgpu_destroy(kgpu_handle *h) {
    if (h->evSnap) cudaEventDestroy(h->evSnap);
    if (h->evCopied) cudaEventDestroy(h->evCopied);
    for (int k = 0; k < 5; k++) cudaFree(h->snap[k]);
+   cudaFree(h->rg.dEntries); cudaFree(h->rg.dPatch); cudaFree(h->rg.dSend); cudaFree(h->rg.dCounts); cudaFree(h->rg.dVslot);
+   cudaFree(h->rg.dCslot); cudaFree(h->rg.dVkey); cudaFree(h->rg.dVbase); cudaFree(h->rg.dCkey); cudaFree(h->rg.dCbase);
    if (h->stream) cudaStreamDestroy(h->stream);
    delete h;
    return 0;

@@ -13,6 +13,7 @@ struct NcclApi {
    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*GroupStart)() = nullptr;
    ncclResult_t (*GroupEnd)() = nullptr;
    const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -32,7 +33,7 @@ static bool loadNccl(std::string &err) {
    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, name));       \
    if (!g_nccl.field) { err = std::string("libnccl lacks ") + name; return false; }
    KSYM(GetUniqueId, "ncclGetUniqueId") KSYM(CommInitRank, "ncclCommInitRank") KSYM(CommDestroy, "ncclCommDestroy")
-   KSYM(Send, "ncclSend") KSYM(Recv, "ncclRecv") KSYM(AllReduce, "ncclAllReduce") KSYM(GroupStart, "ncclGroupStart")
+   KSYM(Send, "ncclSend") KSYM(Recv, "ncclRecv") KSYM(AllReduce, "ncclAllReduce") KSYM(AllGather, "ncclAllGather") KSYM(GroupStart, "ncclGroupStart")
    KSYM(GroupEnd, "ncclGroupEnd") KSYM(GetErrorString, "ncclGetErrorString")
 #undef KSYM
    g_nccl.ok = true;
@@ -126,11 +127,12 @@ static int allreduceCfl(kgpu_handle *h, int slot) {
 }
 
 // the morphodynamic refine flag and the length of the redistribution list (adjacent ints of the control
-// block): every rank must take the same decision (TimeStepper.f90:709-773), so reduce with max
+// block): every rank must take the same decision (TimeStepper.f90:709-773), so reduce with max into the
+// g* pair -- the local list length is still needed afterwards
 static int allreduceMorphoFlags(kgpu_handle *h) {
    if (!h->comm.active) return 0;
    static_assert(offsetof(Ctrl, nRedist) == offsetof(Ctrl, refineMorpho) + sizeof(int), "flags must be adjacent");
-   int *p = &h->d_ctrl->refineMorpho;
-   NCCL_TRY(h, g_nccl.AllReduce(p, p, 2, ncclInt, ncclMax, (ncclComm_t)h->comm.nccl, h->stream));
+   static_assert(offsetof(Ctrl, gRedistMax) == offsetof(Ctrl, gRefine) + sizeof(int), "flags must be adjacent");
+   NCCL_TRY(h, g_nccl.AllReduce(&h->d_ctrl->refineMorpho, &h->d_ctrl->gRefine, 2, ncclInt, ncclMax, (ncclComm_t)h->comm.nccl, h->stream));
    return 0;
 }

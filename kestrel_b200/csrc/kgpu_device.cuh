@@ -74,6 +74,8 @@ struct Ctrl {
    int nonfinite;
    int refineMorpho;               // morphodynamic refine flag
    int nRedist;                    // length of the redistribution list
+   int gRefine;                    // decomposed runs: max over ranks of refineMorpho ...
+   int gRedistMax;                 // ... and of nRedist (the local values above stay intact)
 };
 
 __device__ __forceinline__ int cidx(const DevParams &P, int i, int j) { return (j + YO) * P.pitch + (i + XO); }

@@ -371,4 +371,178 @@ __global__ void morpho_redistribute_kernel(const DevParams P, const RedistArgs A
    }
 }
 
+// ------------------------------------------------------------------ redistribution across ranks
+// RedistributeGrid is one sequential walk over a list sorted over the WHOLE domain (Redistribute.f90:203-247),
+// and every correction changes the bed its neighbours' corrections start from, so a decomposed run cannot
+// process "its" entries independently.  Instead every rank replays the whole global list on a sparse copy of
+// just the data the walk can touch: per listed cell the 4 x 4 vertices and 3 x 3 cells around it ("patch"),
+// packed by the owning rank, all-gathered, and addressed through slot tables the host builds from the cell
+// indices alone (vertices / cells shared by several patches resolve to ONE canonical slot, periodic images
+// included).  All ranks do identical arithmetic in identical order, then each scatters the canonical values
+// that fall into its block.  The arithmetic is that of morpho_redistribute_kernel, statement for statement.
+constexpr int RP_V = 16, RP_C = 9;                    // vertices / cells per patch
+constexpr int RP_B0 = 0, RP_BT0 = 16, RP_BT3 = 32;    // vertex fields
+constexpr int RP_W0 = 48, RP_HPSI0 = 57, RP_W3 = 66, RP_HPSI3 = 75;   // cell fields
+constexpr int RP_DOUBLES = 84;
+
+struct RedistPackArgs {
+   const double *b0v, *bt0, *bt3, *w0, *hpsi0, *w3, *hpsi3;
+   const RedistEntry *list;   // local entries, local indices
+   int n;
+};
+// one thread per (entry, patch element)
+__global__ void redist_pack_kernel(const DevParams P, const RedistPackArgs A, double *out) {
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= A.n * RP_DOUBLES) return;
+   int e = k / RP_DOUBLES, o = k % RP_DOUBLES;
+   int i = A.list[e].i, j = A.list[e].j;
+   const double *src;
+   int a, b;
+   if (o < RP_W0) {
+      src = o < RP_BT0 ? A.b0v : (o < RP_BT3 ? A.bt0 : A.bt3);
+      int q = o % RP_V; a = q % 4 - 1; b = q / 4 - 1;
+   } else {
+      int f = (o - RP_W0) / RP_C;
+      src = f == 0 ? A.w0 : f == 1 ? A.hpsi0 : f == 2 ? A.w3 : A.hpsi3;
+      int q = (o - RP_W0) % RP_C; a = q % 3 - 1; b = q / 3 - 1;
+   }
+   int jj = P.oneD ? 0 : j + b;
+   out[k] = src[(size_t)(jj + YO) * P.pitch + (i + a + XO)];
+}
+
+__device__ __forceinline__ void centreTopoVals(const DevParams &P, double a, double b, double c, double d, double ta, double tb, double tc,
+                                               double td, double &b0c, double &btc, double &bx, double &by) {
+   // centreTopoGlobal (kgpu_tiles.cuh) on values: a = (i,j), b = (i+1,j), c = (i,j+1), d = (i+1,j+1)
+   if (!P.oneD) {
+      b0c = 0.25 * kahan4(a, b, c, d);
+      btc = 0.25 * kahan4(ta, tb, tc, td);
+      bx = 0.5 * P.dxR * kahan8(b, tb, -a, -ta, d, td, -c, -tc);
+      by = 0.5 * P.dyR * kahan8(c, tc, -a, -ta, d, td, -b, -tb);
+   } else {
+      b0c = 0.5 * (a + b);
+      btc = 0.5 * (ta + tb);
+      bx = P.dxR * kahan4(b, tb, -a, -ta);
+      by = 0.0;
+   }
+}
+
+struct RedistGlobalArgs {
+   double *G;            // gathered patches, canonical values live at the slot offsets below
+   const int *vslot;     // [n][16] offset of the b0 value of vertex (i-1+a, j-1+b), a + 4 b; bt0 at +16, bt3 at +32
+   const int *cslot;     // [n][9]  offset of the w0 value of cell (i-1+a, j-1+b), a + 3 b; hpsi0 +9, w3 +18, hpsi3 +27
+   int n;
+   Ctrl *ctrl;
+};
+__global__ void redist_global_kernel(const DevParams P, const RedistGlobalArgs A) {
+   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+   const double EPS = 2.220446049250313e-16;
+   double *G = A.G;
+   const int rowV = P.oneD ? 0 : 4, rowC = P.oneD ? 0 : 3;   // 1-D: every row of the patch is row 0
+   for (int e = 0; e < A.n; e++) {
+      const int *vs = A.vslot + (size_t)e * RP_V, *cs = A.cslot + (size_t)e * RP_C;
+      // the patch rows are j-1, j, j+1(, j+2): the cell itself sits at a = 1, b = 1
+      auto V = [&](int a, int b) -> int { return vs[a + (P.oneD ? 1 : b) * 4]; };
+      auto C = [&](int a, int b) -> int { return cs[a + (P.oneD ? 1 : b) * 3]; };
+      (void)rowV; (void)rowC;
+      auto centre = [&](int a, int b, int fieldOff, double &b0c, double &btc, double &bx, double &by) {
+         int v00 = V(a, b), v10 = V(a + 1, b), v01 = P.oneD ? v00 : V(a, b + 1), v11 = P.oneD ? v10 : V(a + 1, b + 1);
+         centreTopoVals(P, G[v00], G[v10], G[v01], G[v11], G[v00 + fieldOff], G[v10 + fieldOff], G[v01 + fieldOff], G[v11 + fieldOff],
+                        b0c, btc, bx, by);
+      };
+      const int c = C(1, 1);
+      double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
+      centre(1, 1, RP_BT0, b0c, bt0c, bx0, by0);
+      centre(1, 1, RP_BT3, b0c, bt3c, bx3, by3);
+      double gamold = gamma2(P, bx0, by0);
+      double Hn_old = computeHn(G[c], b0c, bt0c, gamold);
+      double corr;
+      excessDeposition(P, G[c + 9], Hn_old, gamold, bt3c - bt0c, corr);
+      if (!(corr > EPS)) continue;
+      double b_diff[4] = {0, 0, 0, 0}, sum_b_diff = 0.0;
+      int dv[4], N = 0;
+      const int oi[4] = {0, 1, 0, 1}, oj[4] = {0, 0, 1, 1};
+      for (int k = 0; k < (P.oneD ? 2 : 4); k++) {
+         int v = V(1 + oi[k], 1 + oj[k]);
+         b_diff[N] = G[v + RP_BT3] - G[v + RP_BT0];
+         if (b_diff[N] > 0.0) { dv[N] = v; sum_b_diff = sum_b_diff + b_diff[N]; N++; }
+      }
+      if (N == 0) { A.ctrl->refineMorpho = 1; return; }
+      double delta = 4.0 * corr / sum_b_diff;
+      double Hnold = Hn_old < 0.0 ? 0.0 : Hn_old;
+      double db = bt3c - bt0c;
+      double tol = EPS * G[c + 18] * 10.0;
+      double adjustment = 0.0;
+      double discrepancy = kahan3(Hnold * gamold, -db, corr);
+      if (fabs(discrepancy) < tol) {
+         adjustment = kahan3(tol, -Hnold * gamold, db);
+         adjustment = adjustment * (4.0 / sum_b_diff);
+         adjustment = adjustment - delta;
+         adjustment = fmax(adjustment, 0.0);
+      }
+      double Hg = G[c + 9] * gamold / (1.0 - P.BedPorosity);
+      tol = EPS * 10.0;
+      discrepancy = kahan3(Hg, -db, corr);
+      if (fabs(discrepancy) < tol) {
+         double adj = kahan3(tol, -Hg, db);
+         adj = adj * (4.0 / sum_b_diff);
+         adj = adj - delta;
+         adjustment = fmax(adjustment, adj);
+      }
+      delta = delta + adjustment;
+      for (int k = 0; k < N; k++) G[dv[k] + RP_BT3] = G[dv[k] + RP_BT3] - delta * b_diff[k];
+      // refresh the surrounding 3^D cells (Redistribute.f90:404-472)
+      for (int a = 0; a < 3; a++)
+         for (int b = (P.oneD ? 1 : 0); b < (P.oneD ? 2 : 3); b++) {
+            const int cc = C(a, b);
+            double c_b0, c_bt0, c_bx0, c_by0, c_bt3, c_bx3, c_by3;
+            centre(a, b, RP_BT0, c_b0, c_bt0, c_bx0, c_by0);
+            centre(a, b, RP_BT3, c_b0, c_bt3, c_bx3, c_by3);
+            double dbc = c_bt3 - c_bt0;
+            double go = gamma2(P, c_bx0, c_by0), gn = gamma2(P, c_bx3, c_by3);
+            double Ho = computeHn(G[cc], c_b0, c_bt0, go);
+            if (Ho < 0.0) Ho = 0.0;
+            double w;
+            if (!P.oneD) {
+               w = c_bt3;
+               w = w + (Ho * go / gn - dbc / gn) / gn;
+               w = w + c_b0;
+            } else {
+               w = -dbc / gn / gn;
+               w = w + Ho * go / gn / gn;
+               w = w + c_bt3;
+               w = w + c_b0;
+            }
+            G[cc + 18] = w;
+            G[cc + 27] = G[cc + 9] * go / gn - (1.0 - P.BedPorosity) * dbc / gn;
+         }
+   }
+}
+
+// canonical values back into the local planes: key = global index, images = every local position it maps to
+struct RedistScatterArgs {
+   const double *G;
+   const int *vkey, *vbase;   // unique vertices: (gi, gj) pairs, slot offset
+   const int *ckey, *cbase;   // unique cells
+   int nv, nc;
+   double *bt3, *w3, *hpsi3;
+   int gx0, gy0, NXg, NYg;    // origin of the local block in global cells, global extent
+};
+__global__ void redist_scatter_kernel(const DevParams P, const RedistScatterArgs A) {
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool isV = k < A.nv;
+   if (!isV) { k -= A.nv; if (k >= A.nc) return; }
+   const int gi = isV ? A.vkey[2 * k] : A.ckey[2 * k], gj = isV ? A.vkey[2 * k + 1] : A.ckey[2 * k + 1];
+   const int base = isV ? A.vbase[k] : A.cbase[k];
+   const int hiX = isV ? P.NX + 2 : P.NX + 1, hiY = P.oneD ? 0 : (isV ? P.NY + 2 : P.NY + 1);
+   for (int oy = -1; oy <= 1; oy++)
+      for (int ox = -1; ox <= 1; ox++) {
+         if (P.oneD && oy != 0) continue;
+         int li = gi - A.gx0 + ox * A.NXg, lj = P.oneD ? 0 : gj - A.gy0 + oy * A.NYg;
+         if (li < -2 || li > hiX || lj < (P.oneD ? 0 : -2) || lj > hiY) continue;
+         size_t g = (size_t)(lj + YO) * P.pitch + (li + XO);
+         if (isV) A.bt3[g] = A.G[base + RP_BT3];
+         else { A.w3[g] = A.G[base + 18]; A.hpsi3[g] = A.G[base + 27]; }
+      }
+}
+
 }  // namespace kgpu

@@ -28,6 +28,130 @@ static int fillHaloPlanes(kgpu_handle *h, double *const *planes, int n, bool ver
    return 0;
 }
 
+// RedistributeGrid across ranks (see kgpu_morpho.cuh): gather the lists and the patches, replay the global
+// walk identically on every rank, scatter the canonical values into the local planes.  The host only
+// sorts indices and builds slot tables -- the same bookkeeping role it has on a single device.
+static int redistributeAcrossRanks(kgpu_handle *h, int nLocal, int M, int R1, int MA) {
+   kgpu_comm &c = h->comm;
+   const bool gather = c.active;   // false: single device driven through the same walk (KGPU_REDIST_GLOBAL=1, test hook)
+   const int R = gather ? c.size : 1;
+   ncclComm_t comm = (ncclComm_t)c.nccl;
+   const size_t tot = (size_t)R * M;
+   RedistGlobalBufs &B = h->rg;
+   if (B.cap < tot) {
+      cudaFree(B.dEntries); cudaFree(B.dPatch); cudaFree(B.dVslot); cudaFree(B.dCslot); cudaFree(B.dVkey); cudaFree(B.dVbase);
+      cudaFree(B.dCkey); cudaFree(B.dCbase);
+      B.cap = tot + tot / 2 + 64;
+      CUDA_TRY(h, cudaMalloc(&B.dEntries, sizeof(RedistEntry) * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dPatch, sizeof(double) * RP_DOUBLES * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dVslot, sizeof(int) * RP_V * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dCslot, sizeof(int) * RP_C * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dVkey, sizeof(int) * 2 * RP_V * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dVbase, sizeof(int) * RP_V * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dCkey, sizeof(int) * 2 * RP_C * B.cap));
+      CUDA_TRY(h, cudaMalloc(&B.dCbase, sizeof(int) * RP_C * B.cap));
+   }
+   if (B.sendCap < M) {
+      cudaFree(B.dSend);
+      B.sendCap = M + M / 2 + 64;
+      CUDA_TRY(h, cudaMalloc(&B.dSend, sizeof(double) * RP_DOUBLES * B.sendCap));
+   }
+   if (!B.dCounts) CUDA_TRY(h, cudaMalloc(&B.dCounts, sizeof(int) * 64));
+   if (R > 64) { h->err = "redistribution across more than 64 ranks"; return KGPU_ERR_UNSUPPORTED; }
+   // 1. list lengths, lists (M entries per rank, the tail beyond a rank's own length is padding) and patches
+   if (gather) {
+      NCCL_TRY(h, g_nccl.AllGather(&h->d_ctrl->nRedist, B.dCounts, 1, ncclInt, comm, h->stream));
+      NCCL_TRY(h, g_nccl.AllGather(h->d_redist, B.dEntries, sizeof(RedistEntry) * (size_t)M, ncclChar, comm, h->stream));
+   } else {
+      CUDA_TRY(h, cudaMemcpyAsync(B.dCounts, &h->d_ctrl->nRedist, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(B.dEntries, h->d_redist, sizeof(RedistEntry) * (size_t)M, cudaMemcpyDeviceToDevice, h->stream));
+   }
+   if (nLocal > 0) {
+      RedistPackArgs pa;
+      pa.b0v = h->b0v; pa.bt0 = h->btv[h->bt0]; pa.bt3 = h->btv[h->bt3];
+      pa.w0 = h->S[R1][QW]; pa.hpsi0 = h->S[R1][QHPSI]; pa.w3 = h->S[MA][QW]; pa.hpsi3 = h->S[MA][QHPSI];
+      pa.list = h->d_redist; pa.n = nLocal;
+      int nthr = nLocal * RP_DOUBLES;
+      redist_pack_kernel<<<(nthr + 255) / 256, 256, 0, h->stream>>>(h->D, pa, B.dSend);
+      h->launches++;
+   }
+   if (gather) NCCL_TRY(h, g_nccl.AllGather(B.dSend, B.dPatch, (size_t)RP_DOUBLES * M, ncclDouble, comm, h->stream));
+   else CUDA_TRY(h, cudaMemcpyAsync(B.dPatch, B.dSend, sizeof(double) * RP_DOUBLES * M, cudaMemcpyDeviceToDevice, h->stream));
+   std::vector<RedistEntry> all(tot);
+   std::vector<int> counts(R);
+   CUDA_TRY(h, cudaMemcpyAsync(all.data(), B.dEntries, sizeof(RedistEntry) * tot, cudaMemcpyDeviceToHost, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(counts.data(), B.dCounts, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   // 2. the global list in the reference's order: ascending excess, ties in scan order = ascending global tile,
+   //    then j, then i (Redistribute.f90:69-101), on GLOBAL indices
+   struct GEntry { double excess; int gi, gj, patch; };
+   std::vector<GEntry> ge;
+   const int NXg = h->nX * h->gnXt, NYg = h->oneD ? 1 : h->nY * h->gnYt;
+   for (int r = 0; r < R; r++) {
+      const int ox = gather ? (r % c.px) * h->NX : 0, oy = gather ? (r / c.px) * h->NY : 0;
+      for (int k = 0; k < counts[r]; k++) {
+         const RedistEntry &e = all[(size_t)r * M + k];
+         ge.push_back({e.excess, e.i + ox, h->oneD ? 0 : e.j + oy, (int)((size_t)r * M + k)});
+      }
+   }
+   const int nX = h->nX, nY = h->nY, gnXt = h->gnXt;
+   std::stable_sort(ge.begin(), ge.end(), [&](const GEntry &x, const GEntry &y) {
+      if (x.excess != y.excess) return x.excess < y.excess;
+      int tx_ = (x.gi / nX) + (x.gj / nY) * gnXt, ty_ = (y.gi / nX) + (y.gj / nY) * gnXt;
+      if (tx_ != ty_) return tx_ < ty_;
+      if (x.gj != y.gj) return x.gj < y.gj;
+      return x.gi < y.gi;
+   });
+   // 3. slot tables: every vertex / cell of every patch resolves to the first patch (in list order) that holds it
+   const int n = (int)ge.size();
+   std::vector<int> vslot((size_t)n * RP_V), cslot((size_t)n * RP_C), vkey, vbase, ckey, cbase;
+   std::unordered_map<long long, int> vmap, cmap;
+   auto wrap = [](int i, int m) { return ((i % m) + m) % m; };
+   for (int e = 0; e < n; e++) {
+      const int pbase = ge[e].patch * RP_DOUBLES;
+      for (int q = 0; q < RP_V; q++) {
+         int gi = wrap(ge[e].gi - 1 + q % 4, NXg), gj = h->oneD ? 0 : wrap(ge[e].gj - 1 + q / 4, NYg);
+         long long key = (long long)gj * NXg + gi;
+         auto it = vmap.find(key);
+         if (it == vmap.end()) {
+            it = vmap.emplace(key, pbase + RP_B0 + q).first;
+            vkey.push_back(gi); vkey.push_back(gj); vbase.push_back(it->second);
+         }
+         vslot[(size_t)e * RP_V + q] = it->second;
+      }
+      for (int q = 0; q < RP_C; q++) {
+         int gi = wrap(ge[e].gi - 1 + q % 3, NXg), gj = h->oneD ? 0 : wrap(ge[e].gj - 1 + q / 3, NYg);
+         long long key = (long long)gj * NXg + gi;
+         auto it = cmap.find(key);
+         if (it == cmap.end()) {
+            it = cmap.emplace(key, pbase + RP_W0 + q).first;
+            ckey.push_back(gi); ckey.push_back(gj); cbase.push_back(it->second);
+         }
+         cslot[(size_t)e * RP_C + q] = it->second;
+      }
+   }
+   CUDA_TRY(h, cudaMemcpyAsync(B.dVslot, vslot.data(), sizeof(int) * vslot.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(B.dCslot, cslot.data(), sizeof(int) * cslot.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(B.dVkey, vkey.data(), sizeof(int) * vkey.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(B.dVbase, vbase.data(), sizeof(int) * vbase.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(B.dCkey, ckey.data(), sizeof(int) * ckey.size(), cudaMemcpyHostToDevice, h->stream));
+   CUDA_TRY(h, cudaMemcpyAsync(B.dCbase, cbase.data(), sizeof(int) * cbase.size(), cudaMemcpyHostToDevice, h->stream));
+   // 4. the walk (one thread, as on a single device) and the scatter
+   RedistGlobalArgs ga;
+   ga.G = B.dPatch; ga.vslot = B.dVslot; ga.cslot = B.dCslot; ga.n = n; ga.ctrl = h->d_ctrl;
+   redist_global_kernel<<<1, 32, 0, h->stream>>>(h->D, ga);
+   RedistScatterArgs sa;
+   sa.G = B.dPatch; sa.vkey = B.dVkey; sa.vbase = B.dVbase; sa.ckey = B.dCkey; sa.cbase = B.dCbase;
+   sa.nv = (int)vbase.size(); sa.nc = (int)cbase.size();
+   sa.bt3 = h->btv[h->bt3]; sa.w3 = h->S[MA][QW]; sa.hpsi3 = h->S[MA][QHPSI];
+   sa.gx0 = gather ? c.rx * h->NX : 0; sa.gy0 = gather ? c.ry * h->NY : 0; sa.NXg = NXg; sa.NYg = NYg;
+   redist_scatter_kernel<<<(sa.nv + sa.nc + 255) / 256, 256, 0, h->stream>>>(h->D, sa);
+   h->launches += 2;
+   CUDA_TRY(h, cudaGetLastError());
+   CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // the host tables go out of scope
+   return 0;
+}
+
 template <bool ONED>
 static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
@@ -107,11 +231,23 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    if ((rc = readCtrl(h))) return rc;
    bool refine = h->h_ctrl->refineMorpho != 0;
    int nRed = h->h_ctrl->nRedist;
-   if (!refine && nRed > 0 && h->comm.active) {
-      // RedistributeGrid walks ONE list sorted over the whole domain and every correction feeds the next
-      // (Redistribute.f90:203-247): a chain may cross any number of blocks.  Not decomposed yet.
-      h->err = "excess deposition must be redistributed (Redistribute.f90:203): not supported in decomposed runs yet";
-      return KGPU_ERR_UNSUPPORTED;
+   if (h->comm.active) {   // every rank takes the decisions of the whole domain
+      const int nLocal = nRed;
+      refine = h->h_ctrl->gRefine != 0;
+      nRed = h->h_ctrl->gRedistMax;
+      if (!refine && nRed > h->redistCap) refine = true;
+      if (!refine && nRed > 0) {
+         if ((rc = redistributeAcrossRanks(h, nLocal, nRed, R1, MA))) return rc;
+         if ((rc = readCtrl(h))) return rc;
+         refine = h->h_ctrl->refineMorpho != 0;   // the walk is replicated: every rank sets the same flag
+      }
+      nRed = 0;   // done (or refining): skip the single-device walk below
+   } else if (!refine && nRed > 0 && nRed <= h->redistCap && h->periodic && allAct && std::getenv("KGPU_REDIST_GLOBAL")) {
+      // test hook: a single periodic device takes the walk the decomposed runs use (tests/test_gpu_parity.py)
+      if ((rc = redistributeAcrossRanks(h, nRed, nRed, R1, MA))) return rc;
+      if ((rc = readCtrl(h))) return rc;
+      refine = h->h_ctrl->refineMorpho != 0;
+      nRed = 0;
    }
    if (!refine && nRed > h->redistCap) refine = true;  // list overflow: treat like a failed redistribution
    if (!refine && nRed > 0) {

@@ -36,6 +36,17 @@ def dambreak_runset(n_tiles: int, per_tile: int = 128, morpho: bool = False, **o
     return rs
 
 
+def thin_dambreak_runset(n_tiles: int, per_tile: int = 32, **over) -> RunSet:
+    """Morphodynamic dam-break in a 5-10 cm layer carrying 30 % solids over a 2 cm bed relief: the deposit
+    soon exceeds what the thin flow holds, so RedistributeGrid (Redistribute.f90:203) runs from about the
+    11th step on -- the workload of the redistribution tests."""
+    rs = dambreak_runset(n_tiles, per_tile, morpho=True, topog_params=[0.02], **over)
+    L = rs.xSize
+    rs.cubes = [Cube(x=0.0, y=0.0, length=L, width=L, height=0.05, psi=0.3, shape="level"),
+                Cube(x=-0.25 * L, y=0.0, length=0.5 * L, width=L, height=0.05, psi=0.3, shape="flat")]
+    return rs
+
+
 def dambreak_state(rs: RunSet, block=None):
     """Initial state of the whole domain, or of one block of the tile grid.
 

@@ -117,6 +117,7 @@ struct Oracle {
    double t, t0, dtgrid;
    int64_t nsteps = 0, nrefines = 0, ntilesAdded = 0;
    int nthreads = 1;
+   int64_t nRedistributed = 0;
    bool haltError = false;
    // loop bounds: bounding box of the active tiles + 2 cells (cells [ilo,ihi) x [jlo,jhi))
    int ilo = 0, ihi = 0, jlo = 0, jhi = 0;
@@ -1590,6 +1591,7 @@ struct Oracle {
             double ex, dBt, psiold;
             excessDeposition(nd.j * NX + nd.i, ex, dBt, psiold);
             if (ex > EPS) {
+               nRedistributed++;   // test diagnostics only (kor_debug_redistributed)
                if (!redistributeCell(nd.i, nd.j, ex)) { refine = true; break; }
             }
          }
@@ -1743,6 +1745,9 @@ int kor_create(const kgpu_params *p, kor_handle **h) {
    return 0;
 }
 int kor_destroy(kor_handle *h) { delete h; return 0; }
+// test diagnostics: how many RedistributeCell calls the run has made so far (lets a test assert that the
+// redistribution path was really exercised)
+int64_t kor_debug_redistributed(const kor_handle *h) { return h ? h->nRedistributed : 0; }
 const char *kor_last_error(const kor_handle *h) { return h ? h->err.c_str() : "null handle"; }
 int kor_set_threads(kor_handle *h, int n) { h->nthreads = n < 1 ? 1 : n; return 0; }
 

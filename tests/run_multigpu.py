@@ -16,7 +16,14 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from kestrel_b200 import capi  # noqa: E402
-from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state, decomposition, rank_block  # noqa: E402
+from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state, decomposition, rank_block, thin_dambreak_runset  # noqa: E402
+
+
+def make_runset(args):
+    if args.thin:
+        args.morpho = True
+        return thin_dambreak_runset(args.tiles, args.per)
+    return dambreak_runset(args.tiles, args.per, morpho=args.morpho)
 
 
 def attach(lib, st, rank, device):
@@ -38,6 +45,7 @@ def main():
     ap.add_argument("--per", type=int, default=64)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--morpho", action="store_true", help="Strang-split run with the morphodynamic operator (bed included in the comparison)")
+    ap.add_argument("--thin", action="store_true", help="thin-layer morphodynamic dam-break: RedistributeGrid runs every step (across ranks)")
     ap.add_argument("--arithmetic", type=int, default=0)
     args = ap.parse_args()
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -46,7 +54,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     lib = capi.load_gpu()
     px, py = decomposition(world)
-    rs = dambreak_runset(args.tiles, args.per, morpho=args.morpho)
+    rs = make_runset(args)
     rs.device = lrank
     rs.arithmetic = args.arithmetic
     rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
@@ -67,7 +75,7 @@ def main():
     dist.gather(tb, bparts, 0)
     ok = True
     if rank == 0:
-        rs1 = dambreak_runset(args.tiles, args.per, morpho=args.morpho)
+        rs1 = make_runset(args)
         rs1.device = lrank
         rs1.arithmetic = args.arithmetic
         Q4, B0 = dambreak_state(rs1)

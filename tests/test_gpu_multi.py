@@ -38,3 +38,17 @@ def test_decomposed_morphodynamic_run_is_bitwise_equal(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_decomposed_redistribution_is_bitwise_equal(world):
+    """RedistributeGrid across ranks (gathered patches, replicated global walk): the thin-layer dam-break
+    redistributes excess deposit every step from the 11th on, with the dam fronts sitting on the rank seams."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29540 + world), os.path.join(ROOT, "tests", "run_multigpu.py"), "--tiles", "4", "--per", "32", "--steps", "20",
+           "--thin"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout

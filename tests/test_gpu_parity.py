@@ -186,6 +186,35 @@ def test_morpho_dambreak_periodic(oracle_lib, gpu_lib):
     assert rel_linf(bg, bo) <= MORPHO_TOL
 
 
+def test_morpho_redistribution_single_and_global_walk(oracle_lib, gpu_lib, monkeypatch):
+    """RedistributeGrid (Redistribute.f90:203-475) on a workload that needs it every step: the device's
+    sequential walk against the oracle, and the sparse global walk the decomposed runs use (patches +
+    canonical slots, kgpu_morpho.cuh) driven on one device -- it must reproduce the plain walk bit for bit."""
+    import ctypes as C
+    from kestrel_b200.host.synthetic import thin_dambreak_runset
+    rs = thin_dambreak_runset(2, 32)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io, ig = so.integrate_to(1e9, 20), sg.integrate_to(1e9, 20)
+    fn = oracle_lib.dll.kor_debug_redistributed
+    fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
+    assert fn(so.h) > 1000, "the workload must exercise the redistribution"
+    assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
+    (qo, bo), (qg, bg) = so.download_domain(True), sg.download_domain(True)
+    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+        assert rel_linf(qg[d], qo[d]) <= MORPHO_TOL, (name, rel_linf(qg[d], qo[d]))
+    assert rel_linf(bg, bo) <= MORPHO_TOL
+    monkeypatch.setenv("KGPU_REDIST_GLOBAL", "1")
+    sh = domain_stepper(gpu_lib, rs, q4, b0v)
+    ih = sh.integrate_to(1e9, 20)
+    monkeypatch.delenv("KGPU_REDIST_GLOBAL")
+    assert (ih.nsteps, ih.nrefines, ih.t) == (ig.nsteps, ig.nrefines, ig.t)
+    qh, bh = sh.download_domain(True)
+    assert np.array_equal(qh, qg) and np.array_equal(bh, bg)
+    so.close(); sg.close(); sh.close()
+
+
 @pytest.mark.parametrize("case,kw", [
     ("case_cap_morpho.txt", dict(tend=4.0, Nout=2)),
     ("case_flat_depositional.txt", dict(tend=2.0, Nout=1)),
