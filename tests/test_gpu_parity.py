@@ -186,25 +186,47 @@ def test_morpho_dambreak_periodic(oracle_lib, gpu_lib):
     assert rel_linf(bg, bo) <= MORPHO_TOL
 
 
-def test_morpho_redistribution_single_and_global_walk(oracle_lib, gpu_lib, monkeypatch):
-    """RedistributeGrid (Redistribute.f90:203-475) on a workload that needs it every step: the device's
-    sequential walk against the oracle, and the sparse global walk the decomposed runs use (patches +
-    canonical slots, kgpu_morpho.cuh) driven on one device -- it must reproduce the plain walk bit for bit."""
+def test_morpho_redistribution_single_and_global_walk(oracle_lib, oracle_fma_lib, gpu_lib, monkeypatch):
+    """RedistributeGrid (Redistribute.f90:203-475) on a workload that needs it from the 11th step on.
+
+    Up to step 10 the usual 1e-10 parity holds.  Once redistribution runs, its `|discrepancy| < 10 eps`
+    branches (Redistribute.f90:330-370) decide on rounding-level quantities and the run is no longer
+    well conditioned: the oracle and its own FMA-contracted build (what gfortran -O2 does to the reference)
+    drift apart by 1e-6 .. 1e-2 within a few steps.  There the criterion is that band: the device must sit
+    no further from the oracle than a few times the reference arithmetic's own contraction sensitivity,
+    with identical step and rollback counts.  The sparse global walk the decomposed runs use (patches +
+    canonical slots, kgpu_morpho.cuh), driven on one device, must reproduce the plain walk bit for bit."""
     import ctypes as C
     from kestrel_b200.host.synthetic import thin_dambreak_runset
     rs = thin_dambreak_runset(2, 32)
     q4, b0v = dambreak_state(rs)
     so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sf = domain_stepper(oracle_fma_lib, rs, q4, b0v)
     sg = domain_stepper(gpu_lib, rs, q4, b0v)
-    io, ig = so.integrate_to(1e9, 20), sg.integrate_to(1e9, 20)
     fn = oracle_lib.dll.kor_debug_redistributed
     fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
-    assert fn(so.h) > 1000, "the workload must exercise the redistribution"
+    names = ["w", "rhoHnu", "rhoHnv", "Hnpsi"]
+    # -- before the first redistribution
+    io, ig = so.integrate_to(1e9, 10), sg.integrate_to(1e9, 10)
+    sf.integrate_to(1e9, 10)
+    assert fn(so.h) == 0
     assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
     (qo, bo), (qg, bg) = so.download_domain(True), sg.download_domain(True)
-    for d, name in enumerate(["w", "rhoHnu", "rhoHnv", "Hnpsi"]):
+    for d, name in enumerate(names):
         assert rel_linf(qg[d], qo[d]) <= MORPHO_TOL, (name, rel_linf(qg[d], qo[d]))
     assert rel_linf(bg, bo) <= MORPHO_TOL
+    # -- ten steps with redistribution
+    io, ig = so.integrate_to(1e9, 10), sg.integrate_to(1e9, 10)
+    sf.integrate_to(1e9, 10)
+    assert fn(so.h) > 1000, "the workload must exercise the redistribution"
+    assert (io.nsteps, io.nrefines) == (ig.nsteps, ig.nrefines)
+    assert abs(io.t - ig.t) <= 1e-12 * io.t
+    (qo, bo), (qg, bg), (qf, bf) = so.download_domain(True), sg.download_domain(True), sf.download_domain(True)
+    for d, name in enumerate(names):
+        band = rel_linf(qf[d], qo[d])
+        assert rel_linf(qg[d], qo[d]) <= 10.0 * band + MORPHO_TOL, (name, rel_linf(qg[d], qo[d]), band)
+    assert rel_linf(bg, bo) <= 10.0 * rel_linf(bf, bo) + MORPHO_TOL
+    # -- the walk of the decomposed runs, on one device
     monkeypatch.setenv("KGPU_REDIST_GLOBAL", "1")
     sh = domain_stepper(gpu_lib, rs, q4, b0v)
     ih = sh.integrate_to(1e9, 20)
@@ -212,7 +234,8 @@ def test_morpho_redistribution_single_and_global_walk(oracle_lib, gpu_lib, monke
     assert (ih.nsteps, ih.nrefines, ih.t) == (ig.nsteps, ig.nrefines, ig.t)
     qh, bh = sh.download_domain(True)
     assert np.array_equal(qh, qg) and np.array_equal(bh, bg)
-    so.close(); sg.close(); sh.close()
+    for st in (so, sf, sg, sh):
+        st.close()
 
 
 @pytest.mark.parametrize("case,kw", [
