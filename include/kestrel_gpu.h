@@ -215,6 +215,15 @@ int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices);
 int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices);
 int kgpu_output_wait(kgpu_handle *h);
 
+/* Test probe (no device needed): the host bookkeeping of RedistributeGrid across ranks -- global walk order
+ * (src/Redistribute.f90:69-101 on global indices) and canonical patch slots.  geometry10 = {ranks, slots per
+ * rank, ranks per row, NX, NY of one block, nXpertile, nYpertile, nXtiles, nYtiles (whole domain), isOneD};
+ * the lists are rank-major with `slots per rank` entries each, counts[r] of them valid, LOCAL cell indices.
+ * Outputs sized for sum(counts) entries: patch[n], vslot[n*16], cslot[n*9]; n_unique2 = {vertices, cells}. */
+int kgpu_debug_redist_tables(const int32_t *geometry10, const int32_t *counts, const double *excess,
+                             const int32_t *li, const int32_t *lj, int32_t *n_out, int32_t *patch,
+                             int32_t *vslot, int32_t *cslot, int32_t *n_unique2);
+
 /* ---- multi-GPU (one process per GPU; 2-D block decomposition of the tile grid) */
 
 /* Bytes of an opaque communicator id (ncclUniqueId). */

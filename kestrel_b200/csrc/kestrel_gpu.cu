@@ -24,6 +24,7 @@
 #include "kgpu_comm.cuh"
 #include "kgpu_hydro.cuh"
 #include "kgpu_morpho.cuh"
+#include "kgpu_redist_tables.hpp"
 #include "kgpu_tiles.cuh"
 
 using namespace kgpu;
@@ -1124,6 +1125,22 @@ int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices) {
    }
    CUDA_TRY(h, cudaEventRecord(h->evCopied, h->copyStream));
    h->outputPending = true;
+   return KGPU_OK;
+}
+
+// Test probe of the host bookkeeping of RedistributeGrid across ranks (kgpu_redist_tables.hpp): no device needed.
+int kgpu_debug_redist_tables(const int32_t *geometry10, const int32_t *counts, const double *excess, const int32_t *li, const int32_t *lj,
+                             int32_t *n_out, int32_t *patch, int32_t *vslot, int32_t *cslot, int32_t *n_unique2) {
+   if (!geometry10 || !counts || !excess || !li || !lj || !n_out) return KGPU_ERR_ARG;
+   RedistGeometry g{geometry10[0], geometry10[1], geometry10[2], geometry10[3], geometry10[4], geometry10[5], geometry10[6], geometry10[7],
+                    geometry10[8], geometry10[9]};
+   RedistTables T;
+   buildRedistTables(g, counts, excess, li, lj, T);
+   *n_out = (int32_t)T.patch.size();
+   if (patch) std::copy(T.patch.begin(), T.patch.end(), patch);
+   if (vslot) std::copy(T.vslot.begin(), T.vslot.end(), vslot);
+   if (cslot) std::copy(T.cslot.begin(), T.cslot.end(), cslot);
+   if (n_unique2) { n_unique2[0] = (int32_t)T.vbase.size(); n_unique2[1] = (int32_t)T.cbase.size(); }
    return KGPU_OK;
 }
 

@@ -82,54 +82,16 @@ static int redistributeAcrossRanks(kgpu_handle *h, int nLocal, int M, int R1, in
    CUDA_TRY(h, cudaMemcpyAsync(all.data(), B.dEntries, sizeof(RedistEntry) * tot, cudaMemcpyDeviceToHost, h->stream));
    CUDA_TRY(h, cudaMemcpyAsync(counts.data(), B.dCounts, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-   // 2. the global list in the reference's order: ascending excess, ties in scan order = ascending global tile,
-   //    then j, then i (Redistribute.f90:69-101), on GLOBAL indices
-   struct GEntry { double excess; int gi, gj, patch; };
-   std::vector<GEntry> ge;
+   // 2. + 3. the global walk order and the slot tables (kgpu_redist_tables.hpp; identical on every rank)
+   std::vector<double> ex(tot);
+   std::vector<int> li(tot), lj(tot);
+   for (size_t k = 0; k < tot; k++) { ex[k] = all[k].excess; li[k] = all[k].i; lj[k] = all[k].j; }
+   RedistGeometry geo{R, M, gather ? c.px : 1, h->NX, h->NY, h->nX, h->nY, h->gnXt, h->gnYt, h->oneD ? 1 : 0};
+   RedistTables T;
+   buildRedistTables(geo, counts.data(), ex.data(), li.data(), lj.data(), T);
+   const int n = (int)T.patch.size();
    const int NXg = h->nX * h->gnXt, NYg = h->oneD ? 1 : h->nY * h->gnYt;
-   for (int r = 0; r < R; r++) {
-      const int ox = gather ? (r % c.px) * h->NX : 0, oy = gather ? (r / c.px) * h->NY : 0;
-      for (int k = 0; k < counts[r]; k++) {
-         const RedistEntry &e = all[(size_t)r * M + k];
-         ge.push_back({e.excess, e.i + ox, h->oneD ? 0 : e.j + oy, (int)((size_t)r * M + k)});
-      }
-   }
-   const int nX = h->nX, nY = h->nY, gnXt = h->gnXt;
-   std::stable_sort(ge.begin(), ge.end(), [&](const GEntry &x, const GEntry &y) {
-      if (x.excess != y.excess) return x.excess < y.excess;
-      int tx_ = (x.gi / nX) + (x.gj / nY) * gnXt, ty_ = (y.gi / nX) + (y.gj / nY) * gnXt;
-      if (tx_ != ty_) return tx_ < ty_;
-      if (x.gj != y.gj) return x.gj < y.gj;
-      return x.gi < y.gi;
-   });
-   // 3. slot tables: every vertex / cell of every patch resolves to the first patch (in list order) that holds it
-   const int n = (int)ge.size();
-   std::vector<int> vslot((size_t)n * RP_V), cslot((size_t)n * RP_C), vkey, vbase, ckey, cbase;
-   std::unordered_map<long long, int> vmap, cmap;
-   auto wrap = [](int i, int m) { return ((i % m) + m) % m; };
-   for (int e = 0; e < n; e++) {
-      const int pbase = ge[e].patch * RP_DOUBLES;
-      for (int q = 0; q < RP_V; q++) {
-         int gi = wrap(ge[e].gi - 1 + q % 4, NXg), gj = h->oneD ? 0 : wrap(ge[e].gj - 1 + q / 4, NYg);
-         long long key = (long long)gj * NXg + gi;
-         auto it = vmap.find(key);
-         if (it == vmap.end()) {
-            it = vmap.emplace(key, pbase + RP_B0 + q).first;
-            vkey.push_back(gi); vkey.push_back(gj); vbase.push_back(it->second);
-         }
-         vslot[(size_t)e * RP_V + q] = it->second;
-      }
-      for (int q = 0; q < RP_C; q++) {
-         int gi = wrap(ge[e].gi - 1 + q % 3, NXg), gj = h->oneD ? 0 : wrap(ge[e].gj - 1 + q / 3, NYg);
-         long long key = (long long)gj * NXg + gi;
-         auto it = cmap.find(key);
-         if (it == cmap.end()) {
-            it = cmap.emplace(key, pbase + RP_W0 + q).first;
-            ckey.push_back(gi); ckey.push_back(gj); cbase.push_back(it->second);
-         }
-         cslot[(size_t)e * RP_C + q] = it->second;
-      }
-   }
+   const std::vector<int> &vslot = T.vslot, &cslot = T.cslot, &vkey = T.vkey, &vbase = T.vbase, &ckey = T.ckey, &cbase = T.cbase;
    CUDA_TRY(h, cudaMemcpyAsync(B.dVslot, vslot.data(), sizeof(int) * vslot.size(), cudaMemcpyHostToDevice, h->stream));
    CUDA_TRY(h, cudaMemcpyAsync(B.dCslot, cslot.data(), sizeof(int) * cslot.size(), cudaMemcpyHostToDevice, h->stream));
    CUDA_TRY(h, cudaMemcpyAsync(B.dVkey, vkey.data(), sizeof(int) * vkey.size(), cudaMemcpyHostToDevice, h->stream));
