@@ -235,7 +235,9 @@ int kgpu_comm_create_id(void *id_out);
  * take the rank's own block (local NX x NY cells, (NX+1) x (NY+1) vertices); 2-cell halos of
  * the four primary fields move by ncclSend/ncclRecv after every stage, overlapped with the
  * interior of the stage kernel, and one ncclAllReduce(min) per dt decision keeps every rank
- * on the same time step.  Round 1: periodic, all tiles active, hydraulic operator only.   */
+ * on the same time step.  The morphodynamic operator exchanges E - D, the stage beds and its
+ * centre planes the same way, max-reduces its refine flags, and replays RedistributeGrid
+ * identically on every rank over all-gathered patches.  Round 1: periodic, all tiles active. */
 int kgpu_comm_attach(kgpu_handle *h, const void *id);
 /* Tile block owned by this handle (0-based global tile coordinates). */
 int kgpu_comm_block(kgpu_handle *h, int32_t *tx0, int32_t *ty0, int32_t *ntx, int32_t *nty);
