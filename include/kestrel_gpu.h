@@ -215,6 +215,19 @@ int kgpu_download_domain(kgpu_handle *h, double *q4, double *bt_vertices);
 int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices);
 int kgpu_output_wait(kgpu_handle *h);
 
+/* ---- analytic topography on the device --------------------
+ * For `Topog Type = Function` inputs (src/TopogFuncs.f90) the library can evaluate the heights of a
+ * tile itself when the tile is activated, instead of calling the heights callback and uploading
+ * the result (src/dem.f90:360-415 GetHeights stays the path for rasters).  Coordinates are those of
+ * src/Grid.f90:339-353 and src/UpdateTiles.f90:288-325; params as given in `Topog params`.  The
+ * algebraic functions reproduce the host's values bit for bit, the transcendental ones to the
+ * rounding of the device's libm.  Call after kgpu_create, before the first upload / tile activation;
+ * func < 0 returns to the callback.                                                            */
+enum { KGPU_TOPOG_FLAT = 0, KGPU_TOPOG_XSLOPE, KGPU_TOPOG_YSLOPE, KGPU_TOPOG_XYSLOPE, KGPU_TOPOG_XSINSLOPE,
+       KGPU_TOPOG_XYSINSLOPE, KGPU_TOPOG_XHUMP, KGPU_TOPOG_XTANH, KGPU_TOPOG_XPARAB, KGPU_TOPOG_XYPARAB,
+       KGPU_TOPOG_XBISLOPE, KGPU_TOPOG_X2SLOPES };
+int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams);
+
 /* Test probe (no device needed): the host bookkeeping of RedistributeGrid across ranks -- global walk order
  * (src/Redistribute.f90:69-101 on global indices) and canonical patch slots.  geometry10 = {ranks, slots per
  * rank, ranks per row, NX, NY of one block, nXpertile, nYpertile, nXtiles, nYtiles (whole domain), isOneD};

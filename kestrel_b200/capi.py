@@ -34,6 +34,10 @@ SWITCHES = {"tanh": 0, "rat3": 1, "cos": 2, "linear": 3, "equal": 4, "0.5": 4, "
             "zero": 5, "1": 6, "one": 6, "step": 7}
 
 
+TOPOG_FUNCS = {"flat": 0, "xslope": 1, "yslope": 2, "xyslope": 3, "xsinslope": 4, "xysinslope": 5, "xhump": 6, "xtanh": 7,
+               "xparab": 8, "xyparab": 9, "xbislope": 10, "x2slopes": 11}
+
+
 class KgpuSource(C.Structure):
     _fields_ = [
         ("x", C.c_double), ("y", C.c_double), ("radius", C.c_double),
@@ -136,6 +140,7 @@ class Library:
             ("comm_attach", C.c_int, [C.c_void_p, C.c_void_p]),
             ("comm_block", C.c_int, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
             ("set_pinned", C.c_int, [C.c_void_p, C.c_int32]),
+            ("set_topography_function", C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_int32]),
             ("output_begin", C.c_int, [C.c_void_p, _dp, _dp]),
             ("output_wait", C.c_int, [C.c_void_p]),
         ]:
@@ -253,6 +258,13 @@ class Stepper:
         btv = np.zeros(((1 if self.oneD else self.NY + 1), self.NX + 1)) if want_bt else None
         self._check(self.lib.download_domain(self.h, _ptr(q4), _ptr(btv)))
         return (q4, btv) if want_bt else q4
+
+    def set_topography_function(self, name: Optional[str], params: Sequence[float] = ()):
+        """Evaluate the analytic topography `name` (Topog function of the input file) on the device for every tile
+        activated from now on; None returns to the heights callback."""
+        func = -1 if name is None else TOPOG_FUNCS[name.lower()]
+        arr = np.ascontiguousarray(list(params), dtype=np.float64)
+        self._check(self.lib.set_topography_function(self.h, func, _ptr(arr) if arr.size else None, int(arr.size)))
 
     def output_begin(self, q4: np.ndarray, btv: Optional[np.ndarray] = None):
         """Asynchronous output gather: device snapshot now, transfer into q4 (and btv) while the next

@@ -144,6 +144,7 @@ struct kgpu_handle {
    cudaEvent_t evSnap = nullptr, evCopied = nullptr;
    bool outputPending = false;
    RedistGlobalBufs rg;
+   TopogFn topogFn = {-1, 0, {0, 0, 0, 0, 0, 0, 0, 0}};   // analytic topography evaluated on the device (func < 0: heights callback)
 
    bool allActive() const { return (int)activeList.size() == nTiles; }
    StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
@@ -462,9 +463,10 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
    int nX = h->nX, nY = h->nY;
    size_t nv = (size_t)(nX + 1) * (nY + 1);
    double *hb = h->h_stage;
+   const bool onDevice = !given && h->topogFn.func >= 0;
    if (given) {
       std::memcpy(hb, given, sizeof(double) * (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1));
-   } else {
+   } else if (!onDevice) {
       if (!h->P.heights) { h->err = "no heights callback registered and no b0_vertices given"; return KGPU_ERR_ARG; }
       if (h->P.heights(h->P.heights_ctx, t0 + 1, hb) != 0) { h->err = "heights callback failed"; return KGPU_ERR_ARG; }
    }
@@ -475,9 +477,12 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
    if (!eL && !(h->periodic && h->nXt == 1)) mask |= 1;
    if (!nL && !(h->periodic && h->nYt == 1)) mask |= 2;
    if (!(eL || nL || neL) && (mask & 1) && (mask & 2)) mask |= 4;
-   CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, hb, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
    int tx, ty; tileXY(h, t0, tx, ty);
    dim3 grid((nX + 1 + 127) / 128, h->oneD ? 1 : nY + 1);
+   if (onDevice) {   // TopogFuncs.f90 at the tile's vertices, straight into the staging buffer (global 1-based tile indices)
+      tile_topog_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->topogFn, h->gtx0 + tx + 1, h->gty0 + ty + 1, h->d_stage);
+      h->launches++;
+   } else CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, hb, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
    tile_vertices_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->b0v, h->d_stage, tx, ty, 1, mask);
    h->launches++;
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage is reused
@@ -1125,6 +1130,15 @@ int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices) {
    }
    CUDA_TRY(h, cudaEventRecord(h->evCopied, h->copyStream));
    h->outputPending = true;
+   return KGPU_OK;
+}
+
+int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams) {
+   if (!h || nparams < 0 || nparams > 8 || (nparams > 0 && !params) || func > KGPU_TOPOG_X2SLOPES) return KGPU_ERR_ARG;
+   static const int need[] = {0, 1, 1, 2, 1, 1, 2, 3, 1, 2, 3, 3};   // parameters each function reads (TopogFuncs.f90)
+   if (func >= 0 && nparams < need[func]) { h->err = "too few topography parameters"; return KGPU_ERR_ARG; }
+   h->topogFn.func = func; h->topogFn.n = nparams;
+   for (int k = 0; k < 8; k++) h->topogFn.p[k] = k < nparams ? params[k] : 0.0;
    return KGPU_OK;
 }
 

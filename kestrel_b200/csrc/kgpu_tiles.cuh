@@ -193,4 +193,58 @@ __global__ void tile_vertices_kernel(const DevParams P, double *vfield, double *
    vfield[g] = stage[k];
 }
 
+// ------------------------------------------------------------------ analytic topography on the device
+// TopogFuncs.f90 evaluated at the vertices of one tile, with the coordinates of Grid.f90:339-353 /
+// UpdateTiles.f90:288-325 (cell centre of local index ii in tile gi: -xSize/2 + dx ((gi-1) nX + ii - 1/2); a vertex
+// is half a cell below its cell, the last one half a cell above the last cell).  Same operation order as the host
+// implementations (kestrel_b200/host/topog.py, host_cpp GetHeights): the algebraic functions give the host's bits,
+// the transcendental ones differ by libm vs libdevice rounding.
+struct TopogFn {
+   int func, n;
+   double p[8];
+};
+__global__ void tile_topog_kernel(const DevParams P, const TopogFn F, int gi, int gj, double *stage) {
+   int li = blockIdx.x * blockDim.x + threadIdx.x;
+   int lj = blockIdx.y;
+   int nvy = P.oneD ? 1 : P.nY + 1;
+   if (li > P.nX || lj >= nvy) return;
+   const double PI = 3.141592653589793238462643383279502884;
+   auto xc = [&](int ii) { return -0.5 * P.xSize + P.dx * ((gi - 1.0) * P.nX + (ii - 0.5)); };
+   auto yc = [&](int jj) { return -0.5 * P.ySize + P.dy * ((gj - 1.0) * P.nY + (jj - 0.5)); };
+   const double X = li < P.nX ? xc(li + 1) - 0.5 * P.dx : xc(P.nX) + 0.5 * P.dx;
+   const double Y = lj < P.nY ? yc(lj + 1) - 0.5 * P.dy : yc(P.nY) + 0.5 * P.dy;
+   const double *p = F.p;
+   double b = 0.0;
+   switch (F.func) {
+      case KGPU_TOPOG_FLAT: b = 0.0; break;
+      case KGPU_TOPOG_XSLOPE: b = p[0] * X; break;
+      case KGPU_TOPOG_YSLOPE: b = p[0] * Y; break;
+      case KGPU_TOPOG_XYSLOPE: b = p[0] * X + p[1] * Y; break;
+      case KGPU_TOPOG_XSINSLOPE: b = p[0] * sin(X * (2.0 * PI / P.xSize)); break;
+      case KGPU_TOPOG_XYSINSLOPE: b = p[0] * sin(X * (2.0 * PI / P.xSize)) * sin(Y * (2.0 * PI / P.ySize)); break;
+      case KGPU_TOPOG_XHUMP: b = (X > -p[1] && X < p[1]) ? 0.5 * p[0] * (1.0 + cos(PI * X / p[1])) : 0.0; break;
+      case KGPU_TOPOG_XTANH: b = p[1] * (1.0 + tanh((X - p[0]) / p[2])); break;
+      case KGPU_TOPOG_XPARAB: b = p[0] * X * X; break;
+      case KGPU_TOPOG_XYPARAB: b = p[0] * X * X + p[1] * Y * Y; break;
+      case KGPU_TOPOG_XBISLOPE: {
+         double phi1 = p[0] * PI / 180.0, phi2 = p[1] * PI / 180.0, lam = p[2];
+         double a1 = tan(phi1), a2 = tan(phi2);
+         b = -0.5 * (a1 + a2) * X + 0.5 * (a1 - a2) * lam * log(cosh(X / lam));
+         break;
+      }
+      case KGPU_TOPOG_X2SLOPES: {
+         double alpha = p[0], beta = p[1], R = p[2];
+         double sa = sqrt(1.0 + alpha * alpha), sb = sqrt(1.0 + beta * beta);
+         double xc0 = (sa - sb) * R / (alpha - beta);
+         double zc0 = (alpha * sb - beta * sa) * R / (alpha - beta);
+         double x1 = xc0 - alpha * R / sa, x2 = xc0 - beta * R / sb;
+         double arc = zc0 - sqrt(fmax(R * R - (X - xc0) * (X - xc0), 0.0));
+         b = X < x1 ? -alpha * X : (X > x2 ? -beta * X : arc);
+         break;
+      }
+      default: break;
+   }
+   stage[(size_t)lj * (P.nX + 1) + li] = b;
+}
+
 }  // namespace kgpu

@@ -76,12 +76,14 @@ def write_solution_txt(rs: RunSet, path: str, tiles: Dict[int, dict]):
 class Simulation:
     """LoadSourceConditions + Run against a library exporting the ABI."""
 
-    def __init__(self, rs: RunSet, lib: capi.Library):
+    def __init__(self, rs: RunSet, lib: capi.Library, device_topography: bool = False):
         self.rs = rs
         self.lib = lib
         self.ic_tiles = load_source_conditions(rs)  # also fills NumCellsInSrc
         p, keep = rs.to_c(make_heights_callback(rs))
         self.stepper = capi.Stepper(lib, p, keep)
+        if device_topography:  # tiles activated during the run get their heights from a kernel, not from the callback
+            self.stepper.set_topography_function(rs.topog_func, rs.topog_params)
         for tid in sorted(self.ic_tiles):
             T = self.ic_tiles[tid]
             self.stepper.upload_tile(tid, T.u, b0v=np.ascontiguousarray(T.b0v), maxima=T.maxima, tfirst=T.tfirst,

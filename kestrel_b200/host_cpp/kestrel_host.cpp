@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -663,6 +664,18 @@ Simulation::Simulation(RunSet rs) : rs_(std::move(rs)) {
    if (rc != KGPU_OK) {
       std::string msg = h_ ? kgpu_last_error(h_) : "kgpu_create failed";
       throw FatalError("kgpu_create: " + msg + " (status " + std::to_string(rc) + "; there is no CPU path)");
+   }
+   // KESTREL_GPU_DEVICE_TOPOGRAPHY=1: tiles activated during the run get the heights of `Topog function` from a kernel
+   // (kgpu_set_topography_function) instead of from the callback above; functions the library does not know keep the callback
+   if (const char *e = std::getenv("KESTREL_GPU_DEVICE_TOPOGRAPHY")) {
+      static const char *names[] = {"flat", "xslope", "yslope", "xyslope", "xsinslope", "xysinslope", "xhump", "xtanh", "xparab", "xyparab",
+                                    "xbislope", "x2slopes"};
+      if (e[0] == '1' && rs_.topog_type == "function")
+         for (int f = 0; f < 12; f++)
+            if (rs_.topog_func == names[f]) {
+               Check(kgpu_set_topography_function(h_, f, rs_.topog_params.data(), (int32_t)rs_.topog_params.size()), "kgpu_set_topography_function");
+               break;
+            }
    }
    for (auto &kv : ic_) {
       Tile &T = kv.second;
