@@ -271,6 +271,20 @@ const char *kgpu_version(void);
    `substep`.  Used by the parity tests to compare a single RHS with the oracle's. */
 int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, double *dt);
 
+/* Test probes (no device needed) of the replicated tile table (kestrel_b200/csrc/kgpu_tile_table.hpp), the
+ * groundwork for dynamic tile activation across ranks: AddTile / AddGhostTiles (src/UpdateTiles.f90:56-78,
+ * 389-481) and the CheckIfNearBoundaries replay (src/TimeStepper.f90:924-1150) on global tile indices.
+ * Tile ids are 1-based as in the reference; flags = 4 bits per global tile (N, S, E, W).  add / replay
+ * return 0, or KGPU_ERR_HALT_BC when a tile outside a `halt` domain was requested; lists() fills ascending
+ * active ids, ghost ids in creation order and the number of device operations requested so far.        */
+typedef struct kgpu_tiletable kgpu_tiletable;
+kgpu_tiletable *kgpu_debug_tiletable_new(int32_t nXtiles, int32_t nYtiles, int32_t periodic, int32_t isOneD, int32_t halt_bc);
+void kgpu_debug_tiletable_free(kgpu_tiletable *t);
+int kgpu_debug_tiletable_add(kgpu_tiletable *t, int32_t tile_id);
+int kgpu_debug_tiletable_replay(kgpu_tiletable *t, const int32_t *flags, int32_t nXpertile, int32_t nYpertile, int32_t tile_buffer);
+int kgpu_debug_tiletable_lists(const kgpu_tiletable *t, int32_t *n_active, int32_t *active, int32_t *n_ghost, int32_t *ghost,
+                               int64_t *n_added, int32_t *n_ops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@
 #include "kgpu_hydro.cuh"
 #include "kgpu_morpho.cuh"
 #include "kgpu_redist_tables.hpp"
+#include "kgpu_tile_table.hpp"
 #include "kgpu_tiles.cuh"
 
 using namespace kgpu;
@@ -1155,6 +1156,38 @@ int kgpu_debug_redist_tables(const int32_t *geometry10, const int32_t *counts, c
    if (vslot) std::copy(T.vslot.begin(), T.vslot.end(), vslot);
    if (cslot) std::copy(T.cslot.begin(), T.cslot.end(), cslot);
    if (n_unique2) { n_unique2[0] = (int32_t)T.vbase.size(); n_unique2[1] = (int32_t)T.cbase.size(); }
+   return KGPU_OK;
+}
+
+// Test probes of the replicated tile table (kgpu_tile_table.hpp): no device needed.
+struct kgpu_tiletable { TileTable T; };
+kgpu_tiletable *kgpu_debug_tiletable_new(int32_t nXtiles, int32_t nYtiles, int32_t periodic, int32_t isOneD, int32_t halt_bc) {
+   if (nXtiles < 1 || nYtiles < 1) return nullptr;
+   kgpu_tiletable *t = new kgpu_tiletable;
+   t->T.init(nXtiles, nYtiles, periodic != 0, isOneD != 0, halt_bc != 0);
+   return t;
+}
+void kgpu_debug_tiletable_free(kgpu_tiletable *t) { delete t; }
+int kgpu_debug_tiletable_add(kgpu_tiletable *t, int32_t tile_id) {
+   if (!t) return KGPU_ERR_ARG;
+   bool ok = t->T.addTile(tile_id - 1, false, true);
+   return ok ? KGPU_OK : (t->T.haltViolation ? KGPU_ERR_HALT_BC : KGPU_ERR_ARG);
+}
+int kgpu_debug_tiletable_replay(kgpu_tiletable *t, const int32_t *flags, int32_t nXpertile, int32_t nYpertile, int32_t tile_buffer) {
+   if (!t || !flags) return KGPU_ERR_ARG;
+   std::vector<int> f(flags, flags + t->T.nTiles());
+   bool ok = t->T.replay(f.data(), nXpertile, nYpertile, tile_buffer);
+   return ok ? KGPU_OK : (t->T.haltViolation ? KGPU_ERR_HALT_BC : KGPU_ERR_ARG);
+}
+int kgpu_debug_tiletable_lists(const kgpu_tiletable *t, int32_t *n_active, int32_t *active, int32_t *n_ghost, int32_t *ghost,
+                               int64_t *n_added, int32_t *n_ops) {
+   if (!t) return KGPU_ERR_ARG;
+   if (n_active) *n_active = (int32_t)t->T.activeList.size();
+   if (active) std::copy(t->T.activeList.begin(), t->T.activeList.end(), active);
+   if (n_ghost) *n_ghost = (int32_t)t->T.ghostList.size();
+   if (ghost) std::copy(t->T.ghostList.begin(), t->T.ghostList.end(), ghost);
+   if (n_added) *n_added = t->T.ntilesAdded;
+   if (n_ops) *n_ops = (int32_t)t->T.ops.size();
    return KGPU_OK;
 }
 
