@@ -128,6 +128,70 @@ def _new_id(lib):
     return hb
 
 
+def decomposed_bitwise_check(lib, dist, torch, rank, world, local_rank, px, py, arithmetic, morpho=False, per_rank=1024, steps=5):
+    """N > 1: `steps` steps of a per_rank^2-cells-per-GPU problem run decomposed over all ranks against the same
+    domain on rank 0's device alone; the gathered blocks must equal the single-device state BIT FOR BIT (the min
+    reduction is exact and order-free, everything else is local: SURVEY 8e).  Returns (ok, detail) on rank 0."""
+    from kestrel_b200 import capi
+    from kestrel_b200.host.settings import Cube
+    from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state, rank_block
+    T = per_rank // 128
+
+    def runset():
+        rs = dambreak_runset(T, 128, morpho=morpho)
+        rs.nXtiles, rs.nYtiles = px * T, py * T
+        rs.Ytilesize = None
+        rs.finalize()
+        Lx, Ly = rs.xSize, rs.ySize
+        conc = 0.1 if morpho else 0.0
+        rs.cubes = [Cube(x=0.0, y=0.0, length=Lx, width=Ly, height=1.0, psi=conc, shape="level"),
+                    Cube(x=-0.25 * Lx, y=0.0, length=0.5 * Lx, width=Ly, height=1.0, psi=conc, shape="flat")]
+        rs.device = local_rank
+        rs.arithmetic = arithmetic
+        return rs
+
+    rs = runset()
+    rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
+    blk = rank_block(rs, rank, px, py)
+    q4, b0v = dambreak_state(rs, blk)
+    p, keep = rs.to_c()
+    st = capi.Stepper(lib, p, keep)
+    n = lib.comm_id_bytes()
+    idt = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.tensor(list(_new_id(lib)), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    rc = lib.comm_attach(st.h, (capi.C.c_ubyte * n)(*idt.cpu().tolist()))
+    assert rc == 0, lib.last_error(st.h)
+    st.upload_domain(q4, b0v)
+    info = st.integrate_to(1e30, steps)
+    mine = torch.from_numpy(st.download_domain()).cuda()
+    st.close()
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    rs1 = runset()
+    q1, b1 = dambreak_state(rs1)
+    p1, keep1 = rs1.to_c()
+    s1 = capi.Stepper(lib, p1, keep1)
+    s1.upload_domain(q1, b1)
+    i1 = s1.integrate_to(1e30, steps)
+    ref = s1.download_domain()
+    s1.close()
+    ok = (info.t, info.nsteps, info.nrefines) == (i1.t, i1.nsteps, i1.nrefines)
+    worst = 0.0
+    for r in range(world):
+        tx0, ty0, ntx, nty = rank_block(rs1, r, px, py)
+        sub = ref[:, ty0 * 128:(ty0 + nty) * 128, tx0 * 128:(tx0 + ntx) * 128]
+        got = parts[r].cpu().numpy()
+        if not np.array_equal(sub, got):
+            ok = False
+            worst = max(worst, float(np.max(np.abs(sub - got))))
+    return ok, {"cells_per_gpu": per_rank * per_rank, "steps": steps, "t": info.t, "max_abs_diff": worst,
+                "arithmetic": "contracted" if arithmetic == 1 else "faithful", "workload": "morpho" if morpho else "hydro"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -136,13 +200,15 @@ def run_reference(args):
     steps = max(1, min(args.steps, 10))
     warm = max(1, min(args.warmup, 2))
     cb = cpu_baseline(steps, warm)
+    serial = cpu_baseline(steps=2, warmup=1, threads=1)   # Kestrel itself is serial
+    cb["serial_value"] = serial["value"]
     line = {"impl": "reference", "metric": "cell-updates/s (fp64)", "value": cb["value"], "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off (BASELINE.json configs[4])",
                        "cells": CPU_SAMPLE_SIZE ** 2, "note": "bounded sample of the 16384^2 workload; the reference's memory model "
                                                                "(7 KB/cell) cannot hold the full size"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "serial_value")},
             "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -165,6 +231,9 @@ def main():
     ap.add_argument("--output-intervals", type=int, default=0,
                     help="extra leg: N output intervals of --steps steps each, blocking kgpu_download_domain against the "
                          "asynchronous kgpu_output_begin / kgpu_output_wait (SURVEY 8f rank 2)")
+    ap.add_argument("--no-bitwise", action="store_true", help="N > 1: skip the decomposed-vs-single-device bitwise check")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --size cells per side per GPU; strong: --size is the side of the GLOBAL domain, split over the ranks")
     ap.add_argument("--no-faithful", action="store_true", help="skip the side measurement of the faithful-arithmetic variant")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -207,22 +276,25 @@ def main():
         tsz = torch.tensor([size], device="cuda", dtype=torch.int64)
         dist.all_reduce(tsz, op=dist.ReduceOp.MIN)
         size = int(tsz.item())
-    # weak scaling: every GPU owns a size x size block of a (px*size) x (py*size) periodic domain
+    # weak scaling: every GPU owns a size x size block of a (px*size) x (py*size) periodic domain;
+    # strong scaling: the size x size domain is split into px x py blocks
     px, py = decomposition(world)
-    T = size // 128
-    rs = dambreak_runset(T, 128, morpho=morpho)
+    strong = args.scaling == "strong" and world > 1
+    Tx, Ty = (size // 128 // px, size // 128 // py) if strong else (size // 128, size // 128)
+    rs = dambreak_runset(Tx, 128, morpho=morpho)
     if world > 1:
-        rs.nXtiles, rs.nYtiles = px * T, py * T
+        rs.nXtiles, rs.nYtiles = px * Tx, py * Ty
         rs.Ytilesize = None
         rs.finalize()
         from kestrel_b200.host.settings import Cube
         Lx, Ly = rs.xSize, rs.ySize
-        rs.cubes = [Cube(x=0.0, y=0.0, length=Lx, width=Ly, height=1.0, psi=0.0, shape="level"),
-                    Cube(x=-0.25 * Lx, y=0.0, length=0.5 * Lx, width=Ly, height=1.0, psi=0.0, shape="flat")]
+        conc = 0.1 if morpho else 0.0
+        rs.cubes = [Cube(x=0.0, y=0.0, length=Lx, width=Ly, height=1.0, psi=conc, shape="level"),
+                    Cube(x=-0.25 * Lx, y=0.0, length=0.5 * Lx, width=Ly, height=1.0, psi=conc, shape="flat")]
         rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
     rs.device = local_rank
     rs.arithmetic = args.arithmetic
-    cells = size * size
+    cells = Tx * 128 * Ty * 128
     q4_np, b0v_np = dambreak_state(rs, rank_block(rs, rank, px, py) if world > 1 else None)
     # pinned host buffers (the Fortran host's arrays stand-in) for the e2e leg
     q4 = torch.from_numpy(q4_np).pin_memory()
@@ -383,6 +455,13 @@ def main():
         other = {"arithmetic": "faithful" if args.arithmetic == 1 else "contracted", "value": cells * world * k2 / (ms2 * 1e-3),
                  "unit": "cell-updates/s", "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3}
 
+    # ---- N > 1: the decomposed run equals the single-device run bit for bit (both arithmetic variants)
+    decomposed = None
+    if world > 1 and not args.no_bitwise:
+        checks = [decomposed_bitwise_check(lib, dist, torch, rank, world, local_rank, px, py, a, morpho=morpho) for a in (args.arithmetic, 1 - args.arithmetic)]
+        if rank == 0:
+            decomposed = {"ok": all(c[0] for c in checks), "runs": [c[1] for c in checks]}
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = cpu_baseline(steps=6, warmup=1, morpho=morpho)
@@ -392,7 +471,7 @@ def main():
 
     if rank == 0:
         line = {"metric": "cell-updates/s (fp64)", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ("synthetic dam-break, periodic, xySinSlope(0.2), Chezy 0.04, erosion off, all tiles active "
                                         "(BASELINE.json configs[4])") if not morpho else
@@ -410,6 +489,9 @@ def main():
                 "other_arithmetic": other}
         if pipelined:
             line["output_intervals"] = pipelined
+        if decomposed is not None:
+            line["decomposed_bitwise"] = decomposed["ok"]
+            line["decomposed_bitwise_runs"] = decomposed["runs"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

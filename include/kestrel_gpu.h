@@ -228,15 +228,6 @@ enum { KGPU_TOPOG_FLAT = 0, KGPU_TOPOG_XSLOPE, KGPU_TOPOG_YSLOPE, KGPU_TOPOG_XYS
        KGPU_TOPOG_XBISLOPE, KGPU_TOPOG_X2SLOPES };
 int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams);
 
-/* Test probe (no device needed): the host bookkeeping of RedistributeGrid across ranks -- global walk order
- * (src/Redistribute.f90:69-101 on global indices) and canonical patch slots.  geometry10 = {ranks, slots per
- * rank, ranks per row, NX, NY of one block, nXpertile, nYpertile, nXtiles, nYtiles (whole domain), isOneD};
- * the lists are rank-major with `slots per rank` entries each, counts[r] of them valid, LOCAL cell indices.
- * Outputs sized for sum(counts) entries: patch[n], vslot[n*16], cslot[n*9]; n_unique2 = {vertices, cells}. */
-int kgpu_debug_redist_tables(const int32_t *geometry10, const int32_t *counts, const double *excess,
-                             const int32_t *li, const int32_t *lj, int32_t *n_out, int32_t *patch,
-                             int32_t *vslot, int32_t *cslot, int32_t *n_unique2);
-
 /* ---- multi-GPU (one process per GPU; 2-D block decomposition of the tile grid) */
 
 /* Bytes of an opaque communicator id (ncclUniqueId). */
@@ -250,7 +241,7 @@ int kgpu_comm_create_id(void *id_out);
  * interior of the stage kernel, and one ncclAllReduce(min) per dt decision keeps every rank
  * on the same time step.  The morphodynamic operator exchanges E - D, the stage beds and its
  * centre planes the same way, max-reduces its refine flags, and replays RedistributeGrid
- * identically on every rank over all-gathered patches.  Round 1: periodic, all tiles active. */
+ * identically on every rank over all-gathered patches.  Periodic, all tiles active. */
 int kgpu_comm_attach(kgpu_handle *h, const void *id);
 /* Tile block owned by this handle (0-based global tile coordinates). */
 int kgpu_comm_block(kgpu_handle *h, int32_t *tx0, int32_t *ty0, int32_t *ntx, int32_t *nty);
@@ -261,29 +252,12 @@ int64_t kgpu_launch_count(const kgpu_handle *h);
 /* Device time (ms) accumulated in the fused RHS kernels since the last reset, and
  * the number of launches, measured with CUDA events on the launching stream. */
 int kgpu_rhs_timing(kgpu_handle *h, double *ms, int64_t *launches, int32_t reset);
+/* Morphodynamic bookkeeping since creation: cells handed to RedistributeGrid (src/Redistribute.f90:203-247)
+ * and how often its list outgrew the device buffer and was enlarged (the reference's list is unbounded). */
+int kgpu_morpho_stats(const kgpu_handle *h, int64_t *redistributed_cells, int64_t *list_enlargements);
 /* Stream the handle launches on (cudaStream_t as void*), for external event timing. */
 void *kgpu_stream(kgpu_handle *h);
 const char *kgpu_version(void);
-
-/* Diagnostics: ONE evaluation of CalculateHydraulicRHS (src/HydraulicRHS.f90:64-137) on the
-   current state, without advancing it: ddtExplicit E4[(4, NY, NX)], ddtImplicit I[(NY, NX)]
-   (either may be NULL) and the advised time step of ComputeAdvisedTimeStep (:141-176) for
-   `substep`.  Used by the parity tests to compare a single RHS with the oracle's. */
-int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, double *dt);
-
-/* Test probes (no device needed) of the replicated tile table (kestrel_b200/csrc/kgpu_tile_table.hpp), the
- * groundwork for dynamic tile activation across ranks: AddTile / AddGhostTiles (src/UpdateTiles.f90:56-78,
- * 389-481) and the CheckIfNearBoundaries replay (src/TimeStepper.f90:924-1150) on global tile indices.
- * Tile ids are 1-based as in the reference; flags = 4 bits per global tile (N, S, E, W).  add / replay
- * return 0, or KGPU_ERR_HALT_BC when a tile outside a `halt` domain was requested; lists() fills ascending
- * active ids, ghost ids in creation order and the number of device operations requested so far.        */
-typedef struct kgpu_tiletable kgpu_tiletable;
-kgpu_tiletable *kgpu_debug_tiletable_new(int32_t nXtiles, int32_t nYtiles, int32_t periodic, int32_t isOneD, int32_t halt_bc);
-void kgpu_debug_tiletable_free(kgpu_tiletable *t);
-int kgpu_debug_tiletable_add(kgpu_tiletable *t, int32_t tile_id);
-int kgpu_debug_tiletable_replay(kgpu_tiletable *t, const int32_t *flags, int32_t nXpertile, int32_t nYpertile, int32_t tile_buffer);
-int kgpu_debug_tiletable_lists(const kgpu_tiletable *t, int32_t *n_active, int32_t *active, int32_t *n_ghost, int32_t *ghost,
-                               int64_t *n_added, int32_t *n_ops);
 
 #ifdef __cplusplus
 }

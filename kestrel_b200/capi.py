@@ -143,6 +143,10 @@ class Library:
             ("set_topography_function", C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_int32]),
             ("output_begin", C.c_int, [C.c_void_p, _dp, _dp]),
             ("output_wait", C.c_int, [C.c_void_p]),
+            ("morpho_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+            ("debug_sequential_walk", C.c_int, [C.c_void_p, C.c_int32]),
+            ("debug_global_walk", C.c_int, [C.c_void_p, C.c_int32]),
+            ("debug_redist_capacity", C.c_int, [C.c_void_p, C.c_int32]),
         ]:
             try:
                 f(name, res, args)
@@ -274,6 +278,12 @@ class Stepper:
 
     def output_wait(self):
         self._check(self.lib.output_wait(self.h))
+
+    def morpho_stats(self):
+        """(cells handed to RedistributeGrid, enlargements of its list buffer) since creation."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.morpho_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_rhs(self, substep: int = 1):
         E = np.zeros((4, self.NY, self.NX))

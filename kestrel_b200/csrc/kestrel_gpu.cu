@@ -21,6 +21,7 @@
 
 #include <cuda.h>
 
+#include "../../include/kestrel_gpu_debug.h"
 #include "kgpu_comm.cuh"
 #include "kgpu_hydro.cuh"
 #include "kgpu_morpho.cuh"
@@ -123,6 +124,10 @@ struct kgpu_handle {
    int *d_tileList = nullptr, *d_flags = nullptr, *h_flags = nullptr;
    RedistEntry *d_redist = nullptr, *h_redist = nullptr;
    int redistCap = 0;
+   int64_t nRedistCells = 0, nRedistGrows = 0;   // cells handed to RedistributeGrid / enlargements of its list buffer
+   bool debugGlobalWalk = false;                 // kgpu_debug_global_walk (kestrel_gpu_debug.h)
+   bool debugSequentialWalk = false;             // kgpu_debug_sequential_walk: one thread walks the list, as the reference does
+   int *d_rankMap = nullptr;                     // redistribution wave: list position per cell + the block ticket
 
    // host tile bookkeeping (UpdateTiles.f90)
    std::vector<int> tstate;  // 0 untouched, 1 ghost, 2 active
@@ -763,6 +768,7 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
+   cudaFree(h->d_rankMap);
    cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
    {
@@ -1011,6 +1017,22 @@ int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertic
    }
    h->activeList.clear(); h->ghostList.clear();
    for (int t0 = 0; t0 < h->nTiles; t0++) { h->tstate[t0] = 2; h->loaded[t0] = 1; h->activeList.push_back(t0 + 1); }
+   // containsSource: a tile with a cell centre inside a source disc, <= as at load (SetSources.f90:367-372);
+   // cell coordinates are the global ones of Grid.f90:339-353 (the device's cellX / cellY)
+   std::fill(h->hasSource.begin(), h->hasSource.end(), 0);
+   for (const DevSource &S : h->src)
+      for (int j = 0; j < h->NY; j++) {
+         const int gj = h->gty0 + j / h->nY + 1, tj = j % h->nY + 1;
+         const double y = -0.5 * h->P.ySize + h->P.deltaY * ((gj - 1.0) * h->nY + (tj - 0.5));
+         const double dy2 = h->oneD ? 0.0 : (y - S.y) * (y - S.y);
+         if (dy2 > S.radius * S.radius) continue;
+         for (int i = 0; i < h->NX; i++) {
+            const int gi = h->gtx0 + i / h->nX + 1, ti = i % h->nX + 1;
+            const double x = -0.5 * h->P.xSize + h->P.deltaX * ((gi - 1.0) * h->nX + (ti - 0.5));
+            const double R2 = h->oneD ? (x - S.x) * (x - S.x) : (x - S.x) * (x - S.x) + dy2;
+            if (R2 <= S.radius * S.radius) h->hasSource[(j / h->nY) * h->nXt + i / h->nX] = 1;
+         }
+      }
    h->masksDirty = true;
    h->firstScan = false;
    h->havePre = false;
@@ -1211,6 +1233,33 @@ int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, doubl
                                     (size_t)h->NX * sizeof(double), h->NY, cudaMemcpyDeviceToHost, h->stream));
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
    if (dt) *dt = (substep == 1) ? h->h_ctrl->dtAdvised : h->h_ctrl->dtAdvised / 0.9;
+   return KGPU_OK;
+}
+
+int kgpu_debug_sequential_walk(kgpu_handle *h, int32_t on) {
+   if (!h) return KGPU_ERR_ARG;
+   h->debugSequentialWalk = on != 0;
+   return KGPU_OK;
+}
+int kgpu_debug_global_walk(kgpu_handle *h, int32_t on) {
+   if (!h) return KGPU_ERR_ARG;
+   h->debugGlobalWalk = on != 0;
+   return KGPU_OK;
+}
+int kgpu_debug_redist_capacity(kgpu_handle *h, int32_t entries) {
+   if (!h || entries < 1 || !h->morpho) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   cudaFree(h->d_redist); cudaFreeHost(h->h_redist);
+   h->d_redist = nullptr; h->h_redist = nullptr;
+   h->redistCap = entries;
+   CUDA_TRY(h, cudaMalloc(&h->d_redist, sizeof(RedistEntry) * (size_t)entries));
+   CUDA_TRY(h, cudaMallocHost(&h->h_redist, sizeof(RedistEntry) * (size_t)entries));
+   return KGPU_OK;
+}
+int kgpu_morpho_stats(const kgpu_handle *h, int64_t *redistributed_cells, int64_t *list_enlargements) {
+   if (!h) return KGPU_ERR_ARG;
+   if (redistributed_cells) *redistributed_cells = h->nRedistCells;
+   if (list_enlargements) *list_enlargements = h->nRedistGrows;
    return KGPU_OK;
 }
 

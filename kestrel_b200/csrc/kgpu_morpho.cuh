@@ -269,19 +269,22 @@ struct RedistArgs {
    Ctrl *ctrl;
 };
 
-// RedistributeGrid / RedistributeCell (Redistribute.f90:203-475): inherently sequential
-// (each correction changes the excess of its neighbours), so one thread walks the sorted list.
-__global__ void morpho_redistribute_kernel(const DevParams P, const RedistArgs A) {
-   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// RedistributeCell (Redistribute.f90:249-475) for one listed cell.  The corrected bed and the refreshed
+// cells are read and written through volatile pointers: in the wave kernel below other threads are
+// correcting cells further away at the same time.  Returns false when the cell has no depositional
+// vertex (the reference then asks for a smaller time step, Redistribute.f90:304-309).
+__device__ __forceinline__ bool redistributeCell(const DevParams &P, const RedistArgs &A, int i, int j) {
    const double EPS = 2.220446049250313e-16;
    const int pitch = P.pitch;
+   volatile double *bt3 = A.bt3, *w3 = A.w3, *hpsi3 = A.hpsi3;
+   const volatile double *bt3r = A.bt3;
    auto vix = [&](int vi, int vj) -> size_t {
       if (P.periodic) { vi = wrapIdx(vi, P.NX, 1); if (!P.oneD) vj = wrapIdx(vj, P.NY, 1); }
       return (size_t)(vj + YO) * pitch + (vi + XO);
    };
    // periodic aliases of a vertex that was just modified (keeps the halo copies current)
    auto storeBt = [&](int vi, int vj, double val) {
-      A.bt3[vix(vi, vj)] = val;
+      bt3[vix(vi, vj)] = val;
       if (P.periodic) {
          int bi = wrapIdx(vi, P.NX, 1), bj = P.oneD ? 0 : wrapIdx(vj, P.NY, 1);
          for (int oj = -1; oj <= 1; oj++)
@@ -289,86 +292,143 @@ __global__ void morpho_redistribute_kernel(const DevParams P, const RedistArgs A
                if (P.oneD && oj != 0) continue;
                int ai = bi + oi * P.NX, aj = bj + oj * P.NY;
                if (ai < -2 || ai > P.NX + 2 || aj < (P.oneD ? 0 : -2) || aj > (P.oneD ? 0 : P.NY + 2)) continue;
-               A.bt3[(size_t)(aj + YO) * pitch + (ai + XO)] = val;
+               bt3[(size_t)(aj + YO) * pitch + (ai + XO)] = val;
             }
       }
    };
-   for (int e = 0; e < A.n; e++) {
-      int i = A.list[e].i, j = A.list[e].j;
-      size_t g = (size_t)(j + YO) * pitch + (i + XO);
-      double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
-      centreTopoGlobal(P, A.b0v, A.bt0, i, j, b0c, bt0c, bx0, by0);
-      centreTopoGlobal(P, A.b0v, A.bt3, i, j, b0c, bt3c, bx3, by3);
-      double gamold = gamma2(P, bx0, by0);
-      double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
-      double corr;
-      excessDeposition(P, A.hpsi0[g], Hn_old, gamold, bt3c - bt0c, corr);
-      if (!(corr > EPS)) continue;
-      // depositional vertices of the cell (Redistribute.f90:276-302)
-      double b_diff[4] = {0, 0, 0, 0}, sum_b_diff = 0.0;
-      int dvi[4], dvj[4], N = 0;
-      const int oi[4] = {0, 1, 0, 1}, oj[4] = {0, 0, 1, 1};
-      for (int k = 0; k < (P.oneD ? 2 : 4); k++) {
-         size_t v = vix(i + oi[k], j + oj[k]);
-         b_diff[N] = A.bt3[v] - A.bt0[v];
-         if (b_diff[N] > 0.0) { dvi[N] = i + oi[k]; dvj[N] = j + oj[k]; sum_b_diff = sum_b_diff + b_diff[N]; N++; }
-      }
-      if (N == 0) { A.ctrl->refineMorpho = 1; return; }
-      double delta = 4.0 * corr / sum_b_diff;
-      double Hnold = Hn_old < 0.0 ? 0.0 : Hn_old;  // intermed0%u(iHn)
-      double db = bt3c - bt0c;
-      double tol = EPS * A.w3[g] * 10.0;
-      double adjustment = 0.0;
-      double discrepancy = kahan3(Hnold * gamold, -db, corr);
-      if (fabs(discrepancy) < tol) {
-         adjustment = kahan3(tol, -Hnold * gamold, db);
-         adjustment = adjustment * (4.0 / sum_b_diff);
-         adjustment = adjustment - delta;
-         adjustment = fmax(adjustment, 0.0);
-      }
-      double Hg = A.hpsi0[g] * gamold / (1.0 - P.BedPorosity);
-      tol = EPS * 10.0;
-      discrepancy = kahan3(Hg, -db, corr);
-      if (fabs(discrepancy) < tol) {
-         double adj = kahan3(tol, -Hg, db);
-         adj = adj * (4.0 / sum_b_diff);
-         adj = adj - delta;
-         adjustment = fmax(adjustment, adj);
-      }
-      delta = delta + adjustment;
-      for (int k = 0; k < N; k++) {
-         size_t v = vix(dvi[k], dvj[k]);
-         storeBt(dvi[k], dvj[k], A.bt3[v] - delta * b_diff[k]);
-      }
-      // refresh the surrounding 3^D cells (Redistribute.f90:404-472)
-      for (int ci = i - 1; ci <= i + 1; ci++)
-         for (int cj = (P.oneD ? 0 : j - 1); cj <= (P.oneD ? 0 : j + 1); cj++) {
-            if (!P.periodic && (ci < 0 || ci >= P.NX || cj < 0 || cj >= P.NY)) continue;
-            int wi = wrapIdx(ci, P.NX, P.periodic), wj = P.oneD ? 0 : wrapIdx(cj, P.NY, P.periodic);
-            if (!cellTileActive(P, A.tileMask, A.allActive, wi, wj)) continue;
-            size_t gc = (size_t)(wj + YO) * pitch + (wi + XO);
-            double c_b0, c_bt0, c_bx0, c_by0, c_bt3, c_bx3, c_by3;
-            centreTopoGlobal(P, A.b0v, A.bt0, wi, wj, c_b0, c_bt0, c_bx0, c_by0);
-            centreTopoGlobal(P, A.b0v, A.bt3, wi, wj, c_b0, c_bt3, c_bx3, c_by3);
-            double dbc = c_bt3 - c_bt0;
-            double go = gamma2(P, c_bx0, c_by0), gn = gamma2(P, c_bx3, c_by3);
-            double Ho = computeHn(A.w0[gc], c_b0, c_bt0, go);
-            if (Ho < 0.0) Ho = 0.0;
-            double w;
-            if (!P.oneD) {
-               w = c_bt3;
-               w = w + (Ho * go / gn - dbc / gn) / gn;
-               w = w + c_b0;
-            } else {
-               w = -dbc / gn / gn;
-               w = w + Ho * go / gn / gn;
-               w = w + c_bt3;
-               w = w + c_b0;
-            }
-            A.w3[gc] = w;
-            A.hpsi3[gc] = A.hpsi0[gc] * go / gn - (1.0 - P.BedPorosity) * dbc / gn;
-         }
+   size_t g = (size_t)(j + YO) * pitch + (i + XO);
+   double b0c, bt0c, bx0, by0, bt3c, bx3, by3;
+   centreTopoGlobal(P, A.b0v, A.bt0, i, j, b0c, bt0c, bx0, by0);
+   centreTopoGlobal(P, A.b0v, bt3r, i, j, b0c, bt3c, bx3, by3);
+   double gamold = gamma2(P, bx0, by0);
+   double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
+   double corr;
+   excessDeposition(P, A.hpsi0[g], Hn_old, gamold, bt3c - bt0c, corr);
+   if (!(corr > EPS)) return true;
+   // depositional vertices of the cell (Redistribute.f90:276-302)
+   double b_diff[4] = {0, 0, 0, 0}, sum_b_diff = 0.0;
+   int dvi[4], dvj[4], N = 0;
+   const int oi[4] = {0, 1, 0, 1}, oj[4] = {0, 0, 1, 1};
+   for (int k = 0; k < (P.oneD ? 2 : 4); k++) {
+      size_t v = vix(i + oi[k], j + oj[k]);
+      b_diff[N] = bt3[v] - A.bt0[v];
+      if (b_diff[N] > 0.0) { dvi[N] = i + oi[k]; dvj[N] = j + oj[k]; sum_b_diff = sum_b_diff + b_diff[N]; N++; }
    }
+   if (N == 0) return false;
+   double delta = 4.0 * corr / sum_b_diff;
+   double Hnold = Hn_old < 0.0 ? 0.0 : Hn_old;  // intermed0%u(iHn)
+   double db = bt3c - bt0c;
+   double tol = EPS * w3[g] * 10.0;
+   double adjustment = 0.0;
+   double discrepancy = kahan3(Hnold * gamold, -db, corr);
+   if (fabs(discrepancy) < tol) {
+      adjustment = kahan3(tol, -Hnold * gamold, db);
+      adjustment = adjustment * (4.0 / sum_b_diff);
+      adjustment = adjustment - delta;
+      adjustment = fmax(adjustment, 0.0);
+   }
+   double Hg = A.hpsi0[g] * gamold / (1.0 - P.BedPorosity);
+   tol = EPS * 10.0;
+   discrepancy = kahan3(Hg, -db, corr);
+   if (fabs(discrepancy) < tol) {
+      double adj = kahan3(tol, -Hg, db);
+      adj = adj * (4.0 / sum_b_diff);
+      adj = adj - delta;
+      adjustment = fmax(adjustment, adj);
+   }
+   delta = delta + adjustment;
+   for (int k = 0; k < N; k++) {
+      size_t v = vix(dvi[k], dvj[k]);
+      storeBt(dvi[k], dvj[k], bt3[v] - delta * b_diff[k]);
+   }
+   // refresh the surrounding 3^D cells (Redistribute.f90:404-472)
+   for (int ci = i - 1; ci <= i + 1; ci++)
+      for (int cj = (P.oneD ? 0 : j - 1); cj <= (P.oneD ? 0 : j + 1); cj++) {
+         if (!P.periodic && (ci < 0 || ci >= P.NX || cj < 0 || cj >= P.NY)) continue;
+         int wi = wrapIdx(ci, P.NX, P.periodic), wj = P.oneD ? 0 : wrapIdx(cj, P.NY, P.periodic);
+         if (!cellTileActive(P, A.tileMask, A.allActive, wi, wj)) continue;
+         size_t gc = (size_t)(wj + YO) * pitch + (wi + XO);
+         double c_b0, c_bt0, c_bx0, c_by0, c_bt3, c_bx3, c_by3;
+         centreTopoGlobal(P, A.b0v, A.bt0, wi, wj, c_b0, c_bt0, c_bx0, c_by0);
+         centreTopoGlobal(P, A.b0v, bt3r, wi, wj, c_b0, c_bt3, c_bx3, c_by3);
+         double dbc = c_bt3 - c_bt0;
+         double go = gamma2(P, c_bx0, c_by0), gn = gamma2(P, c_bx3, c_by3);
+         double Ho = computeHn(A.w0[gc], c_b0, c_bt0, go);
+         if (Ho < 0.0) Ho = 0.0;
+         double w;
+         if (!P.oneD) {
+            w = c_bt3;
+            w = w + (Ho * go / gn - dbc / gn) / gn;
+            w = w + c_b0;
+         } else {
+            w = -dbc / gn / gn;
+            w = w + Ho * go / gn / gn;
+            w = w + c_bt3;
+            w = w + c_b0;
+         }
+         w3[gc] = w;
+         hpsi3[gc] = A.hpsi0[gc] * go / gn - (1.0 - P.BedPorosity) * dbc / gn;
+      }
+   return true;
+}
+
+// RedistributeGrid (Redistribute.f90:203-247) as the reference runs it: one thread walks the sorted list.
+// Kept as the yardstick of the wave kernel below (kgpu_debug_sequential_walk).
+__global__ void morpho_redistribute_kernel(const DevParams P, const RedistArgs A) {
+   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+   for (int e = 0; e < A.n; e++)
+      if (!redistributeCell(P, A, A.list[e].i, A.list[e].j)) { A.ctrl->refineMorpho = 1; return; }
+}
+
+// The same walk, in parallel, with the reference's order preserved where it matters.  Entry e (its position
+// in the sorted list) reads the bed at the vertices (i-1 .. i+2, j-1 .. j+2) and writes the vertices of its
+// own cell and the 3 x 3 cells around it, so two entries commute exactly when their cells are more than two
+// cells apart (Chebyshev distance, through the periodic wrap).  rankMap holds, per listed cell, its list
+// position (INT_MAX elsewhere and once the entry is done): an entry runs as soon as no cell within distance 2
+// carries a smaller rank.  Thread = list position; blocks take a ticket, so every entry a thread can wait
+// for belongs to a block that has already started -- no deadlock -- and the lowest unfinished entry is always
+// runnable.  Results are those of the sequential walk bit for bit (tests/test_gpu_parity.py).
+struct RedistWaveArgs {
+   RedistArgs R;
+   int *rankMap;      // one int per padded cell position, INT_MAX outside a walk
+   int *ticket;       // block ticket counter, zero before the launch
+};
+__global__ void redist_rank_kernel(const DevParams P, const RedistEntry *list, int n, int *rankMap, int *ticket) {
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e == 0) *ticket = 0;
+   if (e < n) rankMap[(size_t)(list[e].j + YO) * P.pitch + (list[e].i + XO)] = e;
+}
+__global__ void __launch_bounds__(128) morpho_redistribute_wave_kernel(const DevParams P, const RedistWaveArgs W) {
+   __shared__ int s_block;
+   if (threadIdx.x == 0) s_block = atomicAdd(W.ticket, 1);
+   __syncthreads();
+   const int e = s_block * blockDim.x + threadIdx.x;
+   if (e >= W.R.n) return;
+   const int i = W.R.list[e].i, j = W.R.list[e].j;
+   volatile int *rank = W.rankMap;
+   volatile int *abortFlag = &W.R.ctrl->refineMorpho;
+   const size_t g = (size_t)(j + YO) * P.pitch + (i + XO);
+   const int INF = 0x7f7f7f7f;   // the value the map is memset to
+   bool done = false;
+   while (!done) {
+      if (*abortFlag) break;
+      bool ready = true;
+      for (int dj = (P.oneD ? 0 : -2); dj <= (P.oneD ? 0 : 2); dj++)
+         for (int di = -2; di <= 2; di++) {
+            int ni = i + di, nj = j + dj;
+            if (P.periodic) { ni = wrapIdx(ni, P.NX, 1); if (!P.oneD) nj = wrapIdx(nj, P.NY, 1); }
+            else if (ni < 0 || ni >= P.NX || nj < 0 || nj >= P.NY) continue;
+            if (ni == i && nj == j) continue;
+            if (rank[(size_t)(nj + YO) * P.pitch + (ni + XO)] < e) ready = false;
+         }
+      if (ready) {
+         __threadfence();   // the data of the finished neighbours is visible before it is read
+         if (!redistributeCell(P, W.R, i, j)) *abortFlag = 1;
+         done = true;
+      }
+   }
+   __threadfence();         // this entry's corrections are visible before its rank is released
+   rank[g] = INF;
 }
 
 // ------------------------------------------------------------------ redistribution across ranks

@@ -191,28 +191,50 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    h->launches += 2;
    if ((rc = allreduceMorphoFlags(h))) return rc;
    if ((rc = readCtrl(h))) return rc;
+   // RedistributeGrid's list is unbounded in the reference (a linked list, Redistribute.f90:69-101): when it
+   // outgrows the device buffer the buffer is enlarged and the (cheap, idempotent) check pass repeated
+   {
+      const int need = h->comm.active ? h->h_ctrl->gRedistMax : h->h_ctrl->nRedist;
+      const bool ref0 = h->comm.active ? h->h_ctrl->gRefine != 0 : h->h_ctrl->refineMorpho != 0;
+      if (!ref0 && need > h->redistCap) {
+         cudaFree(h->d_redist); cudaFreeHost(h->h_redist);
+         h->d_redist = nullptr; h->h_redist = nullptr;
+         h->redistCap = need + need / 2 + 1024;
+         CUDA_TRY(h, cudaMalloc(&h->d_redist, sizeof(RedistEntry) * (size_t)h->redistCap));
+         CUDA_TRY(h, cudaMallocHost(&h->h_redist, sizeof(RedistEntry) * (size_t)h->redistCap));
+         h->nRedistGrows++;
+         ctrl_morpho_reset_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl);
+         c.list = h->d_redist; c.listCap = h->redistCap;
+         if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
+         else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
+         h->launches += 2;
+         if ((rc = allreduceMorphoFlags(h))) return rc;
+         if ((rc = readCtrl(h))) return rc;
+      }
+   }
    bool refine = h->h_ctrl->refineMorpho != 0;
    int nRed = h->h_ctrl->nRedist;
    if (h->comm.active) {   // every rank takes the decisions of the whole domain
       const int nLocal = nRed;
       refine = h->h_ctrl->gRefine != 0;
       nRed = h->h_ctrl->gRedistMax;
-      if (!refine && nRed > h->redistCap) refine = true;
       if (!refine && nRed > 0) {
+         h->nRedistCells += nLocal;
          if ((rc = redistributeAcrossRanks(h, nLocal, nRed, R1, MA))) return rc;
          if ((rc = readCtrl(h))) return rc;
          refine = h->h_ctrl->refineMorpho != 0;   // the walk is replicated: every rank sets the same flag
       }
       nRed = 0;   // done (or refining): skip the single-device walk below
-   } else if (!refine && nRed > 0 && nRed <= h->redistCap && h->periodic && allAct && std::getenv("KGPU_REDIST_GLOBAL")) {
-      // test hook: a single periodic device takes the walk the decomposed runs use (tests/test_gpu_parity.py)
+   } else if (!refine && nRed > 0 && h->periodic && allAct && h->debugGlobalWalk) {
+      // test probe (kgpu_debug_global_walk): a single periodic device takes the walk the decomposed runs use
+      h->nRedistCells += nRed;
       if ((rc = redistributeAcrossRanks(h, nRed, nRed, R1, MA))) return rc;
       if ((rc = readCtrl(h))) return rc;
       refine = h->h_ctrl->refineMorpho != 0;
       nRed = 0;
    }
-   if (!refine && nRed > h->redistCap) refine = true;  // list overflow: treat like a failed redistribution
    if (!refine && nRed > 0) {
+      h->nRedistCells += nRed;
       // sorted ascending by excess, ties in scan order: active-tile order, then j, then i (Redistribute.f90:69-101)
       CUDA_TRY(h, cudaMemcpyAsync(h->h_redist, h->d_redist, sizeof(RedistEntry) * nRed, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -229,8 +251,20 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
       r.w0 = h->S[R1][QW]; r.hpsi0 = h->S[R1][QHPSI]; r.w3 = h->S[MA][QW]; r.hpsi3 = h->S[MA][QHPSI];
       r.b0v = h->b0v; r.bt0 = h->btv[h->bt0]; r.bt3 = h->btv[h->bt3]; r.tileMask = h->d_tileMask; r.list = h->d_redist; r.n = nRed;
       r.allActive = allAct; r.ctrl = h->d_ctrl;
-      morpho_redistribute_kernel<<<1, 32, 0, h->stream>>>(h->D, r);
-      h->launches++;
+      if (h->debugSequentialWalk) {
+         morpho_redistribute_kernel<<<1, 32, 0, h->stream>>>(h->D, r);
+         h->launches++;
+      } else {
+         if (!h->d_rankMap) {   // INT_MAX-like everywhere (0x7f7f7f7f); every walk leaves it that way
+            CUDA_TRY(h, cudaMalloc(&h->d_rankMap, sizeof(int) * (h->fieldElems + 1)));
+            CUDA_TRY(h, cudaMemsetAsync(h->d_rankMap, 0x7f, sizeof(int) * h->fieldElems, h->stream));
+         }
+         RedistWaveArgs wv;
+         wv.R = r; wv.rankMap = h->d_rankMap; wv.ticket = h->d_rankMap + h->fieldElems;
+         redist_rank_kernel<<<(nRed + 255) / 256, 256, 0, h->stream>>>(h->D, h->d_redist, nRed, wv.rankMap, wv.ticket);
+         morpho_redistribute_wave_kernel<<<(nRed + 127) / 128, 128, 0, h->stream>>>(h->D, wv);
+         h->launches += 2;
+      }
       if ((rc = readCtrl(h))) return rc;
       refine = h->h_ctrl->refineMorpho != 0;
    }

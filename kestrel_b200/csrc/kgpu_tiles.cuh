@@ -8,7 +8,9 @@
 namespace kgpu {
 
 // cell-centred topography straight from the global vertex arrays
-__device__ __forceinline__ void centreTopoGlobal(const DevParams &P, const double *b0v, const double *btv, int ci, int cj,
+// (BT: const double * or const volatile double * -- the redistribution wave reads a bed other threads are correcting)
+template <class BT>
+__device__ __forceinline__ void centreTopoGlobal(const DevParams &P, const double *b0v, BT btv, int ci, int cj,
                                                  double &b0c, double &btc, double &bx, double &by) {
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    if (!P.oneD) {

@@ -1804,6 +1804,15 @@ int kor_upload_domain(kor_handle *h, const double *q4, const double *b0_vertices
       }
    o.activeList.clear(); o.ghostList.clear();
    for (int t0_ = 0; t0_ < o.nTiles; t0_++) { o.tstate[t0_] = 2; o.loaded[t0_] = 1; o.activeList.push_back(t0_ + 1); }
+   // containsSource: a tile with a cell centre inside a source disc, <= as at load (SetSources.f90:367-372)
+   std::fill(o.hasSource.begin(), o.hasSource.end(), 0);
+   for (const Source &S : o.src)
+      for (int j = 0; j < o.NY; j++)
+         for (int i = 0; i < o.NX; i++) {
+            double x = o.cellX(i), y = o.cellY(j);
+            double R2 = o.oneD ? (x - S.x) * (x - S.x) : (x - S.x) * (x - S.x) + (y - S.y) * (y - S.y);
+            if (R2 <= S.radius * S.radius) o.hasSource[o.tileOfCell(i, j)] = 1;
+         }
    o.updateBounds();
    for (int j = 0; j < o.NY; j++)
       for (int i = 0; i < o.NX; i++) {

@@ -11,10 +11,13 @@ from kestrel_b200 import capi
 from kestrel_b200 import build as kbuild
 
 
-def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "kestrel_gpu.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(kgpu_[a-z_0-9]+)\s*\(", hdr)))
+def declared_symbols(headers=("kestrel_gpu.h", "kestrel_gpu_debug.h")):
+    out = set()
+    for name in headers:
+        hdr = open(os.path.join(ROOT, "include", name)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        out |= set(re.findall(r"\b(kgpu_[a-z_0-9]+)\s*\(", hdr))
+    return sorted(out)
 
 
 @pytest.fixture(scope="module")
@@ -27,6 +30,12 @@ def test_header_declares_the_expected_entry_points():
     for s in ["kgpu_create", "kgpu_destroy", "kgpu_last_error", "kgpu_upload_tile", "kgpu_integrate_to", "kgpu_active_tiles",
               "kgpu_ghost_tiles", "kgpu_download_tile", "kgpu_upload_domain", "kgpu_download_domain", "kgpu_comm_attach"]:
         assert s in syms
+
+
+def test_public_header_carries_no_test_probes():
+    """The drop-in boundary (kestrel_gpu.h) is free of kgpu_debug_* entry points; they live in kestrel_gpu_debug.h."""
+    assert not [s for s in declared_symbols(("kestrel_gpu.h",)) if "debug" in s]
+    assert any("debug" in s for s in declared_symbols(("kestrel_gpu_debug.h",)))
 
 
 def test_library_exports_every_declared_symbol(built_lib):

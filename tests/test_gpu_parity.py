@@ -186,7 +186,7 @@ def test_morpho_dambreak_periodic(oracle_lib, gpu_lib):
     assert rel_linf(bg, bo) <= MORPHO_TOL
 
 
-def test_morpho_redistribution_single_and_global_walk(oracle_lib, oracle_fma_lib, gpu_lib, monkeypatch):
+def test_morpho_redistribution_single_and_global_walk(oracle_lib, oracle_fma_lib, gpu_lib):
     """RedistributeGrid (Redistribute.f90:203-475) on a workload that needs it from the 11th step on.
 
     Up to step 10 the usual 1e-10 parity holds.  Once redistribution runs, its `|discrepancy| < 10 eps`
@@ -227,14 +227,21 @@ def test_morpho_redistribution_single_and_global_walk(oracle_lib, oracle_fma_lib
         assert rel_linf(qg[d], qo[d]) <= 10.0 * band + MORPHO_TOL, (name, rel_linf(qg[d], qo[d]), band)
     assert rel_linf(bg, bo) <= 10.0 * rel_linf(bf, bo) + MORPHO_TOL
     # -- the walk of the decomposed runs, on one device
-    monkeypatch.setenv("KGPU_REDIST_GLOBAL", "1")
     sh = domain_stepper(gpu_lib, rs, q4, b0v)
+    assert gpu_lib.debug_global_walk(sh.h, 1) == 0
     ih = sh.integrate_to(1e9, 20)
-    monkeypatch.delenv("KGPU_REDIST_GLOBAL")
     assert (ih.nsteps, ih.nrefines, ih.t) == (ig.nsteps, ig.nrefines, ig.t)
     qh, bh = sh.download_domain(True)
     assert np.array_equal(qh, qg) and np.array_equal(bh, bg)
-    for st in (so, sf, sg, sh):
+    # -- and the reference's own form of the walk: one thread, list order (the default is the dependency-ordered wave)
+    ss = domain_stepper(gpu_lib, rs, q4, b0v)
+    assert gpu_lib.debug_sequential_walk(ss.h, 1) == 0
+    is_ = ss.integrate_to(1e9, 20)
+    assert (is_.nsteps, is_.nrefines, is_.t) == (ig.nsteps, ig.nrefines, ig.t)
+    qs, bs = ss.download_domain(True)
+    assert np.array_equal(qs, qg) and np.array_equal(bs, bg)
+    assert sg.morpho_stats()[0] == ss.morpho_stats()[0] > 1000
+    for st in (so, sf, sg, sh, ss):
         st.close()
 
 

@@ -1,0 +1,253 @@
+"""Round-2 parity cases: the benchmarked configurations at SURVEY 8(d)'s parity-subset size, the running
+maxima under a moving bed, RedistributeGrid with closures free of libm calls (where the faithful variant
+must equal the oracle BIT FOR BIT), the enlargement of the redistribution list, and flux sources on the
+bulk upload path.
+
+Bars: arithmetic 0 (faithful) on paths made of + - * / sqrt only: bit-identical.  Closures calling
+tanh / log / pow, and arithmetic 1 (contracted): rel-Linf <= 1e-10 per field (BASELINE.json north_star)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import INPUTS, compare_snapshots, domain_stepper, rel_linf, run_input
+from kestrel_b200.host.synthetic import dambreak_runset, dambreak_state, thin_dambreak_runset
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+NAMES = ["w", "rhoHnu", "rhoHnv", "Hnpsi"]
+# every operation of these closures is + - * / sqrt or a comparison (Closures.f90:365-384 Chezy, :566-578 simple
+# erosion, :332-339 simple deposition, :708-719 step transition, :744-750 no damping)
+PLAIN = dict(drag="chezy", erosion="simple", deposition="simple", erosion_transition="step", morpho_damp="none")
+
+
+def _derived(st):
+    """Hn, psi of every cell as the library's download reports them (u13 components 5 and 8)."""
+    return st.assemble(fields=(4, 7))
+
+
+def _oracle_redistributed(oracle_lib, st):
+    fn = oracle_lib.dll.kor_debug_redistributed
+    fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
+    return fn(st.h)
+
+
+# ------------------------------------------------------------------ C5 parity subset
+C5_STEPS = 200
+
+
+@pytest.fixture(scope="module")
+def c5_oracle(oracle_lib):
+    """1024^2 (8 x 8 tiles of 128^2), 200 steps of the headline workload on the oracle (all host threads)."""
+    rs = dambreak_runset(8, 128)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    if oracle_lib.has("set_threads"):
+        oracle_lib.set_threads(so.h, os.cpu_count() or 1)
+    info = so.integrate_to(1e9, C5_STEPS)
+    out = dict(q=so.download_domain(), d=_derived(so), info=(info.t, info.dt_last, info.nsteps, info.nrefines), q4=q4, b0v=b0v)
+    so.close()
+    return out
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+def test_c5_parity_subset_1024(c5_oracle, gpu_lib, arithmetic):
+    """The bench workload at the parity-subset size: faithful bitwise, contracted 1e-10, on w, rhoHnu, rhoHnv,
+    Hnpsi and on the derived Hn, psi of the download; identical step and rollback counts."""
+    rs = dambreak_runset(8, 128)
+    rs.arithmetic = arithmetic
+    sg = domain_stepper(gpu_lib, rs, c5_oracle["q4"], c5_oracle["b0v"])
+    ig = sg.integrate_to(1e9, C5_STEPS)
+    to, dto, no, ro = c5_oracle["info"]
+    assert (ig.nsteps, ig.nrefines) == (no, ro)
+    qg, dg = sg.download_domain(), _derived(sg)
+    sg.close()
+    if arithmetic == 0:
+        assert (ig.t, ig.dt_last) == (to, dto)
+        for d, name in enumerate(NAMES):
+            assert np.array_equal(qg[d], c5_oracle["q"][d]), (name, rel_linf(qg[d], c5_oracle["q"][d]))
+        assert np.array_equal(dg, c5_oracle["d"])
+    else:
+        assert abs(ig.t - to) <= 1e-12 * to
+        for d, name in enumerate(NAMES):
+            assert rel_linf(qg[d], c5_oracle["q"][d]) <= TOL, (name, rel_linf(qg[d], c5_oracle["q"][d]))
+        assert rel_linf(dg[0], c5_oracle["d"][0]) <= TOL
+        assert np.array_equal(dg[1], c5_oracle["d"][1])   # no solids in this workload: psi == 0 exactly
+
+
+MORPHO_STEPS = 100
+
+
+@pytest.fixture(scope="module")
+def c5_morpho_oracle(oracle_lib):
+    rs = dambreak_runset(4, 128, morpho=True)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    if oracle_lib.has("set_threads"):
+        oracle_lib.set_threads(so.h, os.cpu_count() or 1)
+    info = so.integrate_to(1e9, MORPHO_STEPS)
+    q, b = so.download_domain(True)
+    out = dict(q=q, b=b, d=_derived(so), info=(info.t, info.nsteps, info.nrefines), q4=q4, b0v=b0v)
+    so.close()
+    return out
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+def test_c5_morpho_parity_subset_512(c5_morpho_oracle, gpu_lib, arithmetic):
+    """The morphodynamic bench workload (Variable drag, Mixed erosion, Spearman-Manning: tanh / pow closures) at
+    512^2: every field, the bed and the derived Hn, psi to 1e-10; identical step and rollback counts."""
+    rs = dambreak_runset(4, 128, morpho=True)
+    rs.arithmetic = arithmetic
+    sg = domain_stepper(gpu_lib, rs, c5_morpho_oracle["q4"], c5_morpho_oracle["b0v"])
+    ig = sg.integrate_to(1e9, MORPHO_STEPS)
+    to, no, ro = c5_morpho_oracle["info"]
+    assert (ig.nsteps, ig.nrefines) == (no, ro)
+    assert abs(ig.t - to) <= 1e-12 * to
+    (qg, bg), dg = sg.download_domain(True), _derived(sg)
+    sg.close()
+    for d, name in enumerate(NAMES):
+        assert rel_linf(qg[d], c5_morpho_oracle["q"][d]) <= TOL, (name, rel_linf(qg[d], c5_morpho_oracle["q"][d]))
+    assert np.max(np.abs(c5_morpho_oracle["b"])) > 1e-6
+    assert rel_linf(bg, c5_morpho_oracle["b"]) <= TOL
+    for k, name in enumerate(["Hn", "psi"]):
+        assert rel_linf(dg[k], c5_morpho_oracle["d"][k]) <= TOL, name
+
+
+# ------------------------------------------------------------------ maxima under a moving bed (a26)
+MAXIMA = ["Hnmax", "umax", "emax", "dmax", "psimax"]
+
+
+def _compare_maxima(sa, sb, exact):
+    """All five running maxima (value and time of maximum) and tfirst over every active tile."""
+    worst = {}
+    for k in sorted(sa):
+        ma, mb = sa[k]["maxima"], sb[k]["maxima"]
+        for f, name in enumerate(MAXIMA):
+            if exact:
+                assert np.array_equal(ma[f], mb[f]), (k, name)
+            else:
+                worst[name] = max(worst.get(name, 0.0), rel_linf(ma[f, 0], mb[f, 0]))
+        if exact:
+            assert np.array_equal(sa[k]["tfirst"], sb[k]["tfirst"]), (k, "tfirst")
+    return worst
+
+
+@pytest.mark.parametrize("case,kw", [
+    ("case_cap_morpho_2d.txt", dict(tend=1.5, Nout=3)),
+    ("case_flux_morpho_2d.txt", dict(tend=5.0, Nout=2)),
+])
+def test_maxima_moving_bed_bitwise(oracle_lib, gpu_lib, case, kw):
+    """UpdateMaximum{Heights,Speeds,Erosion,Deposit,SolidsFraction} (TimeStepper.f90:1155-1303) on morphodynamic
+    runs with dynamic tiles at the reference's own tiling: every Strang step goes through the standalone maxima
+    kernel.  With closures free of libm calls the faithful variant equals the oracle bit for bit -- state, bed,
+    all five maxima with their times, tfirst -- at every output."""
+    path = os.path.join(INPUTS, case)
+    sg = run_input(gpu_lib, path, **kw, **PLAIN)
+    so = run_input(oracle_lib, path, **kw, **PLAIN)
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert [(i.nsteps, i.nrefines) for i in sg.infos] == [(i.nsteps, i.nrefines) for i in so.infos]
+    moved = 0.0
+    for a, b in zip(sg.snapshots[1:], so.snapshots[1:]):
+        for name, (err, exact) in compare_snapshots(a, b).items():
+            assert exact, f"{name}: {err}"
+        for k in a:
+            assert np.array_equal(a[k]["bt"], b[k]["bt"])
+            moved = max(moved, float(np.max(np.abs(b[k]["bt"]))))
+        _compare_maxima(a, b, exact=True)
+    last = so.snapshots[-1]
+    assert moved > 1e-8, "the bed must move"
+    assert max(np.max(t["maxima"][2, 0]) for t in last.values()) > 0 or max(np.max(t["maxima"][3, 0]) for t in last.values()) > 0
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+def test_maxima_moving_bed_reference_closures(oracle_lib, gpu_lib, arithmetic):
+    """The same with the input file's own closures (tanh switch / damping / transition, Spearman-Manning powers)
+    and in both arithmetic variants: maxima values to 1e-10, tfirst identical wherever the first-inundation step
+    is not decided by a depth within 1e-10 of the threshold."""
+    path = os.path.join(INPUTS, "case_cap_morpho_2d.txt")
+    kw = dict(tend=1.5, Nout=1)
+    sg = run_input(gpu_lib, path, arithmetic=arithmetic, **kw)
+    so = run_input(oracle_lib, path, **kw)
+    assert list(sg.stepper.active_tiles()) == list(so.stepper.active_tiles())
+    assert (sg.infos[-1].nsteps, sg.infos[-1].nrefines) == (so.infos[-1].nsteps, so.infos[-1].nrefines)
+    a, b = sg.snapshots[-1], so.snapshots[-1]
+    worst = _compare_maxima(a, b, exact=False)
+    for name, err in worst.items():
+        assert err <= TOL, (name, err)
+    nt = sum(t["tfirst"].size for t in b.values())
+    bad = sum(int(np.sum(a[k]["tfirst"] != b[k]["tfirst"])) for k in b)
+    assert bad <= 1e-4 * nt, (bad, nt)
+
+
+# ------------------------------------------------------------------ RedistributeGrid, bit for bit (a22)
+def test_redistribution_bitwise_plain_closures(oracle_lib, gpu_lib):
+    """Thin-layer dam-break with closures free of libm calls: the device's RedistributeGrid (dependency-ordered
+    wave) must stay BIT-IDENTICAL to the oracle's sequential walk through thousands of redistributed cells, in
+    state, bed and step / rollback counts, and hand over the same number of cells."""
+    rs = thin_dambreak_runset(2, 32, **PLAIN)
+    q4, b0v = dambreak_state(rs)
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    for chunk in range(4):
+        io, ig = so.integrate_to(1e9, 10), sg.integrate_to(1e9, 10)
+        assert (io.t, io.dt_last, io.nsteps, io.nrefines) == (ig.t, ig.dt_last, ig.nsteps, ig.nrefines), chunk
+        (qo, bo), (qg, bg) = so.download_domain(True), sg.download_domain(True)
+        for d, name in enumerate(NAMES):
+            assert np.array_equal(qo[d], qg[d]), (chunk, name, rel_linf(qg[d], qo[d]))
+        assert np.array_equal(bo, bg), (chunk, rel_linf(bg, bo))
+    n_or = _oracle_redistributed(oracle_lib, so)
+    assert n_or > 1000
+    # the oracle counts cells whose excess is still positive when their turn comes; the device counts list entries
+    assert sg.morpho_stats()[0] >= n_or
+    so.close(); sg.close()
+
+
+def test_redistribution_list_enlargement(gpu_lib):
+    """A list longer than the device buffer enlarges the buffer (the reference's list is unbounded,
+    Redistribute.f90:69-101) instead of asking for a smaller time step: same bits as with the default buffer."""
+    rs = thin_dambreak_runset(2, 32, **PLAIN)
+    q4, b0v = dambreak_state(rs)
+    sa = domain_stepper(gpu_lib, rs, q4, b0v)
+    sb = domain_stepper(gpu_lib, rs, q4, b0v)
+    assert gpu_lib.debug_redist_capacity(sb.h, 16) == 0
+    ia, ib = sa.integrate_to(1e9, 25), sb.integrate_to(1e9, 25)
+    assert (ia.t, ia.nsteps, ia.nrefines) == (ib.t, ib.nsteps, ib.nrefines)
+    (qa, ba), (qb, bb) = sa.download_domain(True), sb.download_domain(True)
+    assert np.array_equal(qa, qb) and np.array_equal(ba, bb)
+    assert sa.morpho_stats()[1] == 0 and sb.morpho_stats()[1] >= 1
+    assert sa.morpho_stats()[0] == sb.morpho_stats()[0] > 1000
+    sa.close(); sb.close()
+
+
+# ------------------------------------------------------------------ flux sources on the bulk upload path
+def test_upload_domain_with_flux_source(oracle_lib, gpu_lib):
+    """kgpu_upload_domain marks containsSource from the source discs (SetSources.f90:367-372) so that a periodic,
+    all-active run injects the source's volume; bit-identical to the oracle, delivered volume to 1e-10."""
+    from kestrel_b200.host.settings import FluxSource
+    from kestrel_b200.host.sources import centre_topography, gamma
+    rs = dambreak_runset(3, 32)
+    rs.sources = [FluxSource(x=7.0, y=-11.0, radius=6.0, time=[0.0, 1.0e6], flux=[25.0, 25.0], psi=[0.1, 0.1])]
+    rs.finalize()
+    q4, b0v = dambreak_state(rs)
+    # NumCellsInSrc as LoadSourceConditions counts it (<= R^2, SetSources.f90:367-372)
+    x = -0.5 * rs.xSize + rs.deltaX * (np.arange(rs.NX) + 0.5)
+    y = -0.5 * rs.ySize + rs.deltaY * (np.arange(rs.NY) + 0.5)
+    s = rs.sources[0]
+    s.num_cells_in_src = int(np.sum((x[None, :] - s.x) ** 2 + (y[:, None] - s.y) ** 2 <= s.radius ** 2))
+    assert s.num_cells_in_src > 50
+    so = domain_stepper(oracle_lib, rs, q4, b0v)
+    sg = domain_stepper(gpu_lib, rs, q4, b0v)
+    io, ig = so.integrate_to(1e9, 40), sg.integrate_to(1e9, 40)
+    assert (io.t, io.nsteps, io.nrefines) == (ig.t, ig.nsteps, ig.nrefines)
+    qo, qg = so.download_domain(), sg.download_domain()
+    for d, name in enumerate(NAMES):
+        assert np.array_equal(qo[d], qg[d]), (name, rel_linf(qg[d], qo[d]))
+    b0c, _, bx, by = centre_topography(rs, b0v)
+    g2 = gamma(rs, bx, by) ** 2
+    vol0, vol1 = float(np.sum((q4[0] - b0c) * g2)), float(np.sum((qg[0] - b0c) * g2))
+    # strict < R^2 feeds the cells (Equations.f90:523): every counted cell lies strictly inside here
+    delivered = 25.0 * ig.t
+    assert abs((vol1 - vol0) - delivered) / delivered < 1e-9
+    assert np.max(qg[3]) > 0.0
+    so.close(); sg.close()
