@@ -33,7 +33,7 @@ using namespace kgpu;
 
 namespace kgpu {
 // contracted-arithmetic instantiations live in kestrel_stage_fast.cu (compiled with -fmad=true)
-void launch_stage_fast(bool oneD, bool hasBt, bool mm2, dim3 grid, cudaStream_t s, const DevParams &P, const StageArgs &a);
+void launch_stage_fast(bool oneD, bool hasBt, bool mm2, bool spec, dim3 grid, cudaStream_t s, const DevParams &P, const StageArgs &a);
 void stage_fast_set_attributes();
 }  // namespace kgpu
 
@@ -110,6 +110,7 @@ struct kgpu_handle {
    TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
    int prefetchDistance = 0;   // L2 prefetch distance of the stage kernel in CTAs (one resident wave)
    int tune = 0;               // StageArgs::tune bits; bit 3 here: 2-D grid without the block list when every block is listed
+   bool useSpec = true;        // take the (geometric factors, nu == 0) instantiation when the run allows it; KGPU_TUNE bit 6 turns it off
    int nbxAll = 0, nbyAll = 0; // CTA tiles per row / column of the local domain
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
    bool havePre = false;       // S[ia] holds q3 before the implicit correction (quirk Q2)
@@ -306,11 +307,24 @@ static int fillHaloVertices(kgpu_handle *h, double *v) {
    return 0;
 }
 
-template <bool ONED, bool HASBT, int LIM>
+template <bool ONED, bool HASBT, int LIM, int SPEC>
 static void launchStageK(kgpu_handle *h, const StageArgs &a, dim3 grid) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false><<<grid, STAGE_THREADS, G::smemBytes(HASBT, false), h->stream>>>(h->D, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false, SPEC>
+      <<<grid, STAGE_THREADS, G::smemBytes(HASBT, false, stageFluxPlanes(SPEC)), h->stream>>>(h->D, a);
+}
+template <bool ONED, bool HASBT, int LIM, int SPEC>
+static void setStageAttr() {
+   constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
+   using G = StageGeom<BX, BY, ONED>;
+   cudaFuncSetAttribute(hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, false, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)G::smemBytes(true, false, stageFluxPlanes(SPEC)));
+}
+template <bool ONED, int SPEC>
+static void launchStageS(kgpu_handle *h, const StageArgs &a, dim3 grid, bool mm2) {
+   if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2, SPEC>(h, a, grid); else launchStageK<ONED, true, -1, SPEC>(h, a, grid); }
+   else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2, SPEC>(h, a, grid); else launchStageK<ONED, false, -1, SPEC>(h, a, grid); }
 }
 // nblocks CTAs taken from a.blockList, or -- when the list is the whole local domain in row-major order --
 // a 2-D grid whose block indices are the tile coordinates (no dependent load before the TMA issue)
@@ -325,10 +339,12 @@ static void launchStageT(kgpu_handle *h, StageArgs a, int nblocks) {
       grid = dim3(h->nbxAll, h->nbyAll);
    }
    const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
-   if (h->P.arithmetic == 1) { launch_stage_fast(ONED, h->morpho, mm2, grid, h->stream, h->D, a); h->launches++; return; }
-   if (h->morpho) { if (mm2) launchStageK<ONED, true, KGPU_LIM_MINMOD2>(h, a, grid); else launchStageK<ONED, true, -1>(h, a, grid); }
-   else           { if (mm2) launchStageK<ONED, false, KGPU_LIM_MINMOD2>(h, a, grid); else launchStageK<ONED, false, -1>(h, a, grid); }
+   // geometric factors on, no eddy viscosity (the reference's defaults): the instantiation with both compiled in
+   const bool spec = !ONED && h->useSpec && h->D.geom && !(h->D.nu > 0.0);
    h->launches++;
+   if (h->P.arithmetic == 1) { launch_stage_fast(ONED, h->morpho, mm2, spec, grid, h->stream, h->D, a); return; }
+   if (!ONED && spec) launchStageS<false, 1>(h, a, grid, mm2);
+   else launchStageS<ONED, 0>(h, a, grid, mm2);
 }
 
 // Tensor maps for the TMA staging of the stage kernel: every plane is a (rows x pitch) fp64
@@ -912,17 +928,9 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
           cudaMallocHost(&h->h_redist, sizeof(RedistEntry) * h->redistCap) != cudaSuccess) return fail("redist");
    }
    // opt in to > 48 KB dynamic shared memory for the stage kernel
-   {
-      int s2 = (int)StageGeom<BX2, BY2, false>::smemBytes(true, false), s1 = (int)StageGeom<BX1, BY1, true>::smemBytes(true, false);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX2, BY2, false, true, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, false, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, KGPU_LIM_MINMOD2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-      cudaFuncSetAttribute(hydro_stage_kernel<BX1, BY1, true, true, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-   }
+   setStageAttr<false, false, KGPU_LIM_MINMOD2, 0>(); setStageAttr<false, false, -1, 0>(); setStageAttr<false, true, KGPU_LIM_MINMOD2, 0>(); setStageAttr<false, true, -1, 0>();
+   setStageAttr<false, false, KGPU_LIM_MINMOD2, 1>(); setStageAttr<false, false, -1, 1>(); setStageAttr<false, true, KGPU_LIM_MINMOD2, 1>(); setStageAttr<false, true, -1, 1>();
+   setStageAttr<true, false, KGPU_LIM_MINMOD2, 0>(); setStageAttr<true, false, -1, 0>(); setStageAttr<true, true, KGPU_LIM_MINMOD2, 0>(); setStageAttr<true, true, -1, 0>();
    stage_fast_set_attributes();
    // topography planes (bt planes only when the bed moves)
    {
@@ -940,6 +948,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
       h->tune = 31;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0, bit 4 +2.2 %; all five +7.9 %
       if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)
+      h->useSpec = !(h->tune & 64);
    }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;

@@ -10,33 +10,39 @@ namespace kgpu {
 
 constexpr int FBX2 = 32, FBY2 = KGPU_STAGE_BY2, FBX1 = 128, FBY1 = 1;
 
-template <bool ONED, bool HASBT, int LIM>
+template <bool ONED, bool HASBT, int LIM, int SPEC>
 static void launchFastK(dim3 nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
    constexpr int BX = ONED ? FBX1 : FBX2, BY = ONED ? FBY1 : FBY2;
    using G = StageGeom<BX, BY, ONED>;
-   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true><<<nblocks, KGPU_STAGE_THREADS, G::smemBytes(HASBT, true), s>>>(P, a);
+   hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true, SPEC>
+      <<<nblocks, KGPU_STAGE_THREADS, G::smemBytes(HASBT, true, stageFluxPlanes(SPEC)), s>>>(P, a);
 }
 
-void launch_stage_fast(bool oneD, bool hasBt, bool mm2, dim3 nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
+// spec: geometric factors on and no eddy viscosity -- the 2-D instantiation that has both as compile-time constants
+void launch_stage_fast(bool oneD, bool hasBt, bool mm2, bool spec, dim3 nblocks, cudaStream_t s, const DevParams &P, const StageArgs &a) {
    if (oneD) {
-      if (hasBt) { if (mm2) launchFastK<true, true, KGPU_LIM_MINMOD2>(nblocks, s, P, a); else launchFastK<true, true, -1>(nblocks, s, P, a); }
-      else       { if (mm2) launchFastK<true, false, KGPU_LIM_MINMOD2>(nblocks, s, P, a); else launchFastK<true, false, -1>(nblocks, s, P, a); }
+      if (hasBt) { if (mm2) launchFastK<true, true, KGPU_LIM_MINMOD2, 0>(nblocks, s, P, a); else launchFastK<true, true, -1, 0>(nblocks, s, P, a); }
+      else       { if (mm2) launchFastK<true, false, KGPU_LIM_MINMOD2, 0>(nblocks, s, P, a); else launchFastK<true, false, -1, 0>(nblocks, s, P, a); }
+   } else if (spec) {
+      if (hasBt) { if (mm2) launchFastK<false, true, KGPU_LIM_MINMOD2, 1>(nblocks, s, P, a); else launchFastK<false, true, -1, 1>(nblocks, s, P, a); }
+      else       { if (mm2) launchFastK<false, false, KGPU_LIM_MINMOD2, 1>(nblocks, s, P, a); else launchFastK<false, false, -1, 1>(nblocks, s, P, a); }
    } else {
-      if (hasBt) { if (mm2) launchFastK<false, true, KGPU_LIM_MINMOD2>(nblocks, s, P, a); else launchFastK<false, true, -1>(nblocks, s, P, a); }
-      else       { if (mm2) launchFastK<false, false, KGPU_LIM_MINMOD2>(nblocks, s, P, a); else launchFastK<false, false, -1>(nblocks, s, P, a); }
+      if (hasBt) { if (mm2) launchFastK<false, true, KGPU_LIM_MINMOD2, 0>(nblocks, s, P, a); else launchFastK<false, true, -1, 0>(nblocks, s, P, a); }
+      else       { if (mm2) launchFastK<false, false, KGPU_LIM_MINMOD2, 0>(nblocks, s, P, a); else launchFastK<false, false, -1, 0>(nblocks, s, P, a); }
    }
 }
 
+template <bool ONED, bool HASBT, int LIM, int SPEC>
+static void setAttr() {
+   constexpr int BX = ONED ? FBX1 : FBX2, BY = ONED ? FBY1 : FBY2;
+   using G = StageGeom<BX, BY, ONED>;
+   cudaFuncSetAttribute(hydro_stage_kernel<BX, BY, ONED, HASBT, LIM, true, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)G::smemBytes(true, true, stageFluxPlanes(SPEC)));
+}
 void stage_fast_set_attributes() {
-   int s2 = (int)StageGeom<FBX2, FBY2, false>::smemBytes(true, true), s1 = (int)StageGeom<FBX1, FBY1, true>::smemBytes(true, true);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, false, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, false, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, true, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX2, FBY2, false, true, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX1, FBY1, true, false, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX1, FBY1, true, false, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX1, FBY1, true, true, KGPU_LIM_MINMOD2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
-   cudaFuncSetAttribute(hydro_stage_kernel<FBX1, FBY1, true, true, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+   setAttr<false, false, KGPU_LIM_MINMOD2, 0>(); setAttr<false, false, -1, 0>(); setAttr<false, true, KGPU_LIM_MINMOD2, 0>(); setAttr<false, true, -1, 0>();
+   setAttr<false, false, KGPU_LIM_MINMOD2, 1>(); setAttr<false, false, -1, 1>(); setAttr<false, true, KGPU_LIM_MINMOD2, 1>(); setAttr<false, true, -1, 1>();
+   setAttr<true, false, KGPU_LIM_MINMOD2, 0>(); setAttr<true, false, -1, 0>(); setAttr<true, true, KGPU_LIM_MINMOD2, 0>(); setAttr<true, true, -1, 0>();
 }
 
 }  // namespace kgpu

@@ -1,0 +1,184 @@
+"""The reference's own acceptance suite (tests/runall.jl:4-56, tests/testlib.jl:106-407) at FULL LENGTH through
+the GPU path: every input runs to its own `T end` with its own `N out` through kestrel_gpu_run (the C++ host
+above the C-ABI), and the checks read the text outputs by the column contract the reference's scripts use
+(testlib.jl:463-474: Hn = column 3 / 6, u = 5 / 8, Hn psi = 9 / 14, bt = 12 / 17 in 1-D / 2-D).
+
+  test_flow_consistency (testlib.jl:18-45):  check_conservativity (:106-158, relative 1e-10, flux sources
+      integrated as in :163-283), check_positivity (:286-302, Hn >= -1e-14), check_max_ero_depth (:306-328)
+  test_no_flow (:47-63):  check_no_flow (:332-358): the printed (x, Hn) pairs of every output are those of 000000.txt
+  test_identical_simulations (:65-95):  check_identical_simulations (:363-407): max-norm distance of the
+      Hn-sorted (Hn, u, Hn psi, bt) rows, 1e-13 static / 1e-11 dynamic (runall.jl:45-46)
+
+These are the only checks the reference itself ships for this path; the oracle is not involved here."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import INPUTS
+from kestrel_b200 import build as kbuild
+
+pytestmark = pytest.mark.gpu
+
+TESTS_1D = ["flat_depositional", "cap_dilute", "cap_conc", "cap_morpho", "flux_hydro", "flux_edwards2019", "flux_morpho"]
+TESTS_2D = ["flat_depositional_2d", "cap_dilute_2d", "cap_conc_2d", "cap_morpho_2d", "flux_hydro_2d", "flux_edwards2019_2d",
+            "flux_morpho_2d", "flux_single_pt"]
+TESTS_NOFLOW = [("lake_at_rest_hydro", 1), ("lake_at_rest_morpho", 1), ("lake_at_rest_hydro_2d", 2), ("lake_at_rest_morpho_2d", 2)]
+TESTS_IDENTICAL = [("tile_indep_static_100m", "tile_indep_static_50m", 1e-13), ("tile_indep_dynamic_100m", "tile_indep_dynamic_20m", 1e-11)]
+
+
+@pytest.fixture(scope="module")
+def driver(gpu_lib):
+    return kbuild.build_host()
+
+
+def run_case(driver, name, out, arithmetic):
+    path = os.path.join(INPUTS, f"case_{name}.txt")
+    r = subprocess.run([driver, path, "-o", str(out), "--arithmetic", str(arithmetic), "--quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return path
+
+
+# ---- readers
+def result_files(d):
+    return sorted(f for f in os.listdir(d) if re.fullmatch(r"\d+\.txt", f))
+
+
+def load_rows(path):
+    rows = [ln for ln in open(path).read().splitlines() if ln.strip()]
+    return np.array([[float(x) for x in ln.split(",")] for ln in rows])
+
+
+def setting(infile, key, default=None):
+    for ln in open(infile):
+        ln = ln.split("%")[0]
+        if "=" in ln and ln.split("=")[0].strip().lower() == key:
+            return ln.split("=", 1)[1].strip()
+    return default
+
+
+def series(txt):
+    return [float(x) for x in txt.strip().strip("()").split(",")]
+
+
+def integrate_source_time_series(t, Q, psi, tstart, tend):
+    """testlib.jl:237-283."""
+    total, solids = 0.0, 0.0
+    if len(t) == 1 and t[0] < tend:
+        total = Q[0] * min(tend - tstart, tend - t[0])
+        solids = psi[0] * total
+    for i in range(len(t) - 1):
+        if t[i + 1] < tstart or t[i] > tend:
+            continue
+        dQ, dp = (Q[i + 1] - Q[i]) / (t[i + 1] - t[i]), (psi[i + 1] - psi[i]) / (t[i + 1] - t[i])
+        tl, tu, Ql, Qu, pl, pu = t[i], t[i + 1], Q[i], Q[i + 1], psi[i], psi[i + 1]
+        if t[i] < tstart:
+            tl, Ql, pl = tstart, Q[i] + dQ * (tstart - t[i]), psi[i] + dp * (tstart - t[i])
+        if t[i + 1] > tend:
+            tu, Qu, pu = tend, Q[i] + dQ * (tend - t[i]), psi[i] + dp * (tend - t[i])
+        dt = tu - tl
+        total += dt * (Ql + Qu) / 2
+        solids += (dt / 6) * (Ql * pu + Qu * pl + 2 * (Ql * pl + Qu * pu))
+    return total, solids
+
+
+def total_flux_sources(infile):
+    """testlib.jl:163-209: every Source block's series integrated over [t start, t end]."""
+    tstart, tend = float(setting(infile, "t start", "0")), float(setting(infile, "t end"))
+    blocks, cur = [], None
+    for ln in open(infile):
+        ln = ln.split("%")[0].strip().lower()
+        if ln.endswith(":"):
+            cur = {} if ln == "source:" else None
+            if cur is not None:
+                blocks.append(cur)
+        elif cur is not None and "=" in ln:
+            k, v = [s.strip() for s in ln.split("=", 1)]
+            cur[k] = v
+    Qt, Qpt = 0.0, 0.0
+    for b in blocks:
+        if "sourcetime" not in b:
+            continue
+        Q, Qp = integrate_source_time_series(series(b["sourcetime"]), series(b["sourceflux"]), series(b["sourceconc"]), tstart, tend)
+        Qt, Qpt = Qt + Q, Qpt + Qp
+    return Qt, Qpt
+
+
+# ---- the reference's checks
+def check_conservativity(d, infile):
+    rows = [[float(x) for x in ln.split(",")] for ln in open(os.path.join(d, "Volume.txt")).read().splitlines()[1:]]
+    first, last = rows[0], rows[-1]
+    flux_vol, flux_sol = total_flux_sources(infile)
+    expected_vol, final_vol = flux_vol + first[1] + first[2], last[1] + last[2]
+    vol_err = abs((expected_vol - final_vol) / expected_vol)
+    rhos = float(setting(infile, "rhos", "2000.0"))
+    expected_sol, final_sol = flux_sol + (first[5] + first[6]) / rhos, (last[5] + last[6]) / rhos
+    sol_err = abs(expected_sol - final_sol) if expected_sol == 0.0 else abs((expected_sol - final_sol) / expected_sol)
+    assert vol_err <= 1e-10, ("volume", vol_err)
+    assert sol_err <= 1e-10, ("solids", sol_err)
+
+
+def check_positivity_and_depth(d, infile, dim):
+    Hn_col, bt_col = (2, 11) if dim == 1 else (5, 16)
+    ero = float(setting(infile, "erosion depth", "0.0"))
+    for f in result_files(d):
+        rows = load_rows(os.path.join(d, f))
+        assert rows[:, Hn_col].min() >= -1e-14, (f, rows[:, Hn_col].min())
+        assert rows[:, bt_col].min() >= -ero, (f, rows[:, bt_col].min())
+
+
+def check_no_flow(d, dim):
+    Hn_col = 2 if dim == 1 else 5
+
+    def pairs(path):
+        return {(c[1].strip(), c[Hn_col].strip()) for c in (ln.split(",") for ln in open(path).read().splitlines() if ln.strip())}
+
+    first = pairs(os.path.join(d, "000000.txt"))
+    for f in result_files(d)[1:]:
+        assert pairs(os.path.join(d, f)) <= first, f"depth field in {f} differs from the initial condition"
+
+
+def check_identical(d1, d2, tol, dim=2):
+    idx = [5, 7, 13, 16] if dim == 2 else [2, 4, 8, 11]
+    f1, f2 = result_files(d1), result_files(d2)
+    assert f1 == f2
+    for f in f1:
+        a, b = load_rows(os.path.join(d1, f))[:, idx], load_rows(os.path.join(d2, f))[:, idx]
+        a, b = a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])]   # sortslices(dims = 1): rows in lexicographic order
+        n = min(len(a), len(b))
+        diff = float(np.max(np.abs(a[len(a) - n:] - b[len(b) - n:])))
+        assert diff <= tol, (f, diff)
+
+
+# ---- the suite
+@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("name", TESTS_1D)
+def test_flow_consistency_1d(driver, tmp_path, name, arithmetic):
+    infile = run_case(driver, name, tmp_path / name, arithmetic)
+    check_conservativity(tmp_path / name, infile)
+    check_positivity_and_depth(tmp_path / name, infile, 1)
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("name", TESTS_2D)
+def test_flow_consistency_2d(driver, tmp_path, name, arithmetic):
+    infile = run_case(driver, name, tmp_path / name, arithmetic)
+    check_conservativity(tmp_path / name, infile)
+    check_positivity_and_depth(tmp_path / name, infile, 2)
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("name,dim", TESTS_NOFLOW)
+def test_no_flow(driver, tmp_path, name, dim, arithmetic):
+    run_case(driver, name, tmp_path / name, arithmetic)
+    check_no_flow(tmp_path / name, dim)
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("a,b,tol", TESTS_IDENTICAL)
+def test_identical_simulations(driver, tmp_path, a, b, tol, arithmetic):
+    run_case(driver, a, tmp_path / a, arithmetic)
+    run_case(driver, b, tmp_path / b, arithmetic)
+    check_identical(tmp_path / a, tmp_path / b, tol)

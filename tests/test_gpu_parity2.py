@@ -163,8 +163,9 @@ def test_maxima_moving_bed_bitwise(oracle_lib, gpu_lib, case, kw):
 @pytest.mark.parametrize("arithmetic", [0, 1])
 def test_maxima_moving_bed_reference_closures(oracle_lib, gpu_lib, arithmetic):
     """The same with the input file's own closures (tanh switch / damping / transition, Spearman-Manning powers)
-    and in both arithmetic variants: maxima values to 1e-10, tfirst identical wherever the first-inundation step
-    is not decided by a depth within 1e-10 of the threshold."""
+    and in both arithmetic variants: maxima values to 1e-10; their times and tfirst name the same steps (dt, and
+    with it every time stamp, carries the 1e-12-relative difference of the runs, so times are compared to 1e-10 of
+    the run length -- a different step would be off by a whole dt, 1e-2 here)."""
     path = os.path.join(INPUTS, "case_cap_morpho_2d.txt")
     kw = dict(tend=1.5, Nout=1)
     sg = run_input(gpu_lib, path, arithmetic=arithmetic, **kw)
@@ -175,9 +176,11 @@ def test_maxima_moving_bed_reference_closures(oracle_lib, gpu_lib, arithmetic):
     worst = _compare_maxima(a, b, exact=False)
     for name, err in worst.items():
         assert err <= TOL, (name, err)
-    nt = sum(t["tfirst"].size for t in b.values())
-    bad = sum(int(np.sum(a[k]["tfirst"] != b[k]["tfirst"])) for k in b)
-    assert bad <= 1e-4 * nt, (bad, nt)
+    for k in b:
+        assert np.max(np.abs(a[k]["tfirst"] - b[k]["tfirst"])) <= TOL * kw["tend"], k
+        assert np.array_equal(a[k]["tfirst"] == -1, b[k]["tfirst"] == -1)
+        for f, name in enumerate(MAXIMA):
+            assert np.max(np.abs(a[k]["maxima"][f, 1] - b[k]["maxima"][f, 1])) <= TOL * kw["tend"], (k, name)
 
 
 # ------------------------------------------------------------------ RedistributeGrid, bit for bit (a22)

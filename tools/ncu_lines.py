@@ -16,8 +16,17 @@ top = int(sys.argv[5]) if len(sys.argv) > 5 else 60
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 lines = out.splitlines()
-start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+# a report with several captured launches prints one table per launch: KERNEL_INDEX (env, default 0) picks one
+import os
+starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')]
+ki = int(os.environ.get("KERNEL_INDEX", "0"))
+start = starts[ki]
+stop = len(lines)
+for j in range(start + 1, len(lines)):
+    if not lines[j].startswith('"0x'):
+        stop = j
+        break
+rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:stop]))))
 
 txt = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout.splitlines()
 on = False
@@ -86,6 +95,23 @@ if rng:
                 name = b
         agg[name] += v
         aggops[name].update(opsouter[(f, ln)])
+    stallcols = [c for c in rows[0].keys() if c.startswith("stall_") and not c.endswith("(Not Issued)")]
+    phase_stall = collections.defaultdict(collections.Counter)
+    phase_samples = collections.Counter()
+    for r, (cur, stack, op) in zip(rows[:n], info[:n]):
+        ln = (stack or cur)[1] if (stack or cur) else 0
+        name = "pre"
+        for a, b in marks:
+            if ln >= a:
+                name = b
+        phase_samples[name] += int(r["# Samples"] or 0)
+        for c in stallcols:
+            phase_stall[name][c] += int(r[c] or 0)
+    tsamp = sum(phase_samples.values())
+    print("--- warp-state samples by phase (share of all samples; top stall reasons within the phase)")
+    for k, v in phase_samples.most_common():
+        top5 = ", ".join(f"{c[6:]} {100.0 * x / max(v, 1):.0f}%" for c, x in phase_stall[k].most_common(6))
+        print(f"{k:8s} {100.0 * v / max(tsamp, 1):5.1f}% of samples: {top5}")
     print("--- by phase")
     for k, v in agg.most_common():
         print(f"{k:8s} {v / cells:7.3f}/cell {100.0 * v / tot:5.1f}%  {dict((o, round(c / cells, 2)) for o, c in aggops[k].most_common(14))}")
