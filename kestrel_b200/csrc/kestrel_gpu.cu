@@ -110,6 +110,7 @@ struct kgpu_handle {
    TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
    int prefetchDistance = 0;   // L2 prefetch distance of the stage kernel in CTAs (one resident wave)
    int tune = 0;               // StageArgs::tune bits; bit 3 here: 2-D grid without the block list when every block is listed
+   int persistCtas = 444;      // resident CTAs of the stage kernel on this device (3 per SM)
    bool useSpec = true;        // take the (geometric factors, nu == 0) instantiation when the run allows it; KGPU_TUNE bit 6 turns it off
    int nbxAll = 0, nbyAll = 0; // CTA tiles per row / column of the local domain
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
@@ -331,13 +332,14 @@ static void launchStageS(kgpu_handle *h, const StageArgs &a, dim3 grid, bool mm2
 template <bool ONED>
 static void launchStageT(kgpu_handle *h, StageArgs a, int nblocks) {
    if (nblocks <= 0) return;
-   dim3 grid(nblocks);
+   // persistent CTAs: one resident wave (3 CTAs per SM) walks all the tiles, each CTA requesting its next tile's boxes
+   // while it finishes the current one; KGPU_TUNE bit 7 launches one CTA per tile instead (the round-1 schedule)
+   dim3 grid((h->tune & 128) ? nblocks : std::min(nblocks, h->persistCtas));
+   a.nTiles = nblocks;
    a.directNbx = 0;
    a.tune = h->tune & ~8;
-   if ((h->tune & 8) && a.blockList == h->d_blockList && nblocks == h->nbxAll * h->nbyAll && h->nbyAll <= 65535) {
-      a.directNbx = h->nbxAll;
-      grid = dim3(h->nbxAll, h->nbyAll);
-   }
+   // every block listed, in row-major order: tile t is block (t % nbx, t / nbx), no list read before the TMA issue
+   if ((h->tune & 8) && a.blockList == h->d_blockList && nblocks == h->nbxAll * h->nbyAll) a.directNbx = h->nbxAll;
    const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
    // geometric factors on, no eddy viscosity (the reference's defaults): the instantiation with both compiled in
    const bool spec = !ONED && h->useSpec && h->D.geom && !(h->D.nu > 0.0);
@@ -660,13 +662,28 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    Update1Args u;
    for (int d = 0; d < 4; d++) { u.q0[d] = h->S[kq0][d]; u.E[d] = h->E0[d]; u.q1[d] = h->S[ka][d]; }
    u.I = h->I0; u.tileMask = h->d_tileMask; u.blockList = h->d_blockList; u.ctrl = h->d_ctrl; u.allActive = h->allActive() ? 1 : 0;
-   if (h->nBlocks) {
-      if (h->oneD) stage1_update_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, u);
-      else stage1_update_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, u);
-      h->launches++;
-   }
    int rc;
-   if ((rc = fillHaloCells(h, ka))) return rc;
+   auto update1 = [&](const int2 *list, int n) {
+      if (n <= 0) return;
+      u.blockList = list;
+      if (h->oneD) stage1_update_kernel<BX1, BY1><<<n, NTHREADS, 0, h->stream>>>(h->D, u);
+      else stage1_update_kernel<BX2, BY2><<<n, NTHREADS, 0, h->stream>>>(h->D, u);
+      h->launches++;
+   };
+   if (h->comm.active) {
+      // edge blocks first: their strips travel on the communication stream while the interior is updated, exactly
+      // as in the fused stages (launchStage); stage 2 waits for the halo event
+      update1(h->d_blockBoundary, h->nBoundary);
+      CUDA_TRY(h, cudaEventRecord(h->comm.evBoundary, h->stream));
+      CUDA_TRY(h, cudaStreamWaitEvent(h->comm.stream, h->comm.evBoundary, 0));
+      if ((rc = exchangeHalo(h, h->S[ka], 4, false, h->comm.stream))) return rc;
+      CUDA_TRY(h, cudaEventRecord(h->comm.evHalo, h->comm.stream));
+      update1(h->d_blockInterior, h->nInterior);
+      CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->comm.evHalo, 0));
+   } else {
+      update1(h->d_blockList, h->nBlocks);
+      if ((rc = fillHaloCells(h, ka))) return rc;
+   }
    if ((rc = launchStage(h, MODE_STAGE2, ka, kb, kq0, kbt))) return rc;
    if ((rc = allreduceCfl(h, 1))) return rc;
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 1);
@@ -945,6 +962,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       int nsm = 148;
       if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) nsm = prop.multiProcessorCount;
       h->prefetchDistance = 3 * nsm;
+      h->persistCtas = KGPU_STAGE_MINBLOCKS * nsm;
       if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
       h->tune = 31;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0, bit 4 +2.2 %; all five +7.9 %
       if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)

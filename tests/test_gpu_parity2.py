@@ -180,7 +180,10 @@ def test_maxima_moving_bed_reference_closures(oracle_lib, gpu_lib, arithmetic):
         assert np.max(np.abs(a[k]["tfirst"] - b[k]["tfirst"])) <= TOL * kw["tend"], k
         assert np.array_equal(a[k]["tfirst"] == -1, b[k]["tfirst"] == -1)
         for f, name in enumerate(MAXIMA):
-            assert np.max(np.abs(a[k]["maxima"][f, 1] - b[k]["maxima"][f, 1])) <= TOL * kw["tend"], (k, name)
+            late = np.abs(a[k]["maxima"][f, 1] - b[k]["maxima"][f, 1]) > TOL * kw["tend"]
+            # faithful: the same step everywhere.  contracted: a maximum that two consecutive steps reach to within
+            # the 1e-10 of the value planes may be stamped with either step (observed: 1 cell of 10 000)
+            assert np.sum(late) <= (0 if arithmetic == 0 else 1e-3 * late.size), (k, name, int(np.sum(late)))
 
 
 # ------------------------------------------------------------------ RedistributeGrid, bit for bit (a22)
