@@ -43,7 +43,9 @@ module kestrel_gpu
    integer(c_int32_t), parameter :: KGPU_TOPOG_FLAT = 0, KGPU_TOPOG_XSLOPE = 1, KGPU_TOPOG_YSLOPE = 2, &
                                     KGPU_TOPOG_XYSLOPE = 3, KGPU_TOPOG_XSINSLOPE = 4, KGPU_TOPOG_XYSINSLOPE = 5, &
                                     KGPU_TOPOG_XHUMP = 6, KGPU_TOPOG_XTANH = 7, KGPU_TOPOG_XPARAB = 8, &
-                                    KGPU_TOPOG_XYPARAB = 9, KGPU_TOPOG_XBISLOPE = 10, KGPU_TOPOG_X2SLOPES = 11
+                                    KGPU_TOPOG_XYPARAB = 9, KGPU_TOPOG_XBISLOPE = 10, KGPU_TOPOG_X2SLOPES = 11, &
+                                    KGPU_TOPOG_USGS = 12, KGPU_TOPOG_FLUME = 13, KGPU_TOPOG_CHANNEL_POWERLAW = 14, &
+                                    KGPU_TOPOG_CHANNEL_TRAPEZIUM = 15, KGPU_TOPOG_XTRISLOPE = 16
 
    ! ---- struct kgpu_source: mirror of type Sources (src/RunSettings.f90:101-109)
    type, bind(C) :: kgpu_source

@@ -225,8 +225,34 @@ int kgpu_output_wait(kgpu_handle *h);
  * func < 0 returns to the callback.                                                            */
 enum { KGPU_TOPOG_FLAT = 0, KGPU_TOPOG_XSLOPE, KGPU_TOPOG_YSLOPE, KGPU_TOPOG_XYSLOPE, KGPU_TOPOG_XSINSLOPE,
        KGPU_TOPOG_XYSINSLOPE, KGPU_TOPOG_XHUMP, KGPU_TOPOG_XTANH, KGPU_TOPOG_XPARAB, KGPU_TOPOG_XYPARAB,
-       KGPU_TOPOG_XBISLOPE, KGPU_TOPOG_X2SLOPES };
+       KGPU_TOPOG_XBISLOPE, KGPU_TOPOG_X2SLOPES, KGPU_TOPOG_USGS, KGPU_TOPOG_FLUME, KGPU_TOPOG_CHANNEL_POWERLAW,
+       KGPU_TOPOG_CHANNEL_TRAPEZIUM, KGPU_TOPOG_XTRISLOPE };
 int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams);
+
+/* ---- initial conditions on the device ------------------------
+ * LoadSourceConditions (src/SetSources.f90:47-392) inside the library: the caps and cubes of the input file are
+ * rasterised on the device instead of on the host followed by one kgpu_upload_tile per tile.  Every tile with a
+ * cell centre inside a cap (R2 <= R^2), a cube or a flux-source disc is switched on through the library's
+ * AddTile (heights from the callback or from kgpu_set_topography_function) in the reference's tile order; the
+ * shapes are then added cell by cell in the reference's order (caps, then cubes) and operation order, including
+ * its quirks (1-D flat caps, 1-D parabolic momentum, psimax in 1-D: src/SetSources.f90:132-144); containsSource
+ * and NumCellsInSrc (:367-372) are set from the handle's source table, the first tile-activation scan is seeded
+ * from the rasterised depth (src/TimeStepper.f90:982).  With bcs = halt a shape that reaches an edge tile returns
+ * KGPU_ERR_HALT_BC (src/UpdateTiles.f90:63-65).  num_cells_in_src (n_sources entries) may be NULL.
+ * Call once, after kgpu_create (and kgpu_set_topography_function), instead of the kgpu_upload_tile calls. */
+enum { KGPU_SHAPE_FLAT = 0, KGPU_SHAPE_PARA = 1, KGPU_SHAPE_LEVEL = 2 };
+typedef struct kgpu_cap {      /* type Caps, src/RunSettings.f90:56-66 */
+   double x, y, radius, height, u, v, psi;
+   int32_t shape;              /* KGPU_SHAPE_* */
+   int32_t _pad;
+} kgpu_cap;
+typedef struct kgpu_cube {     /* type Cubes, src/RunSettings.f90:78-88 */
+   double x, y, length, width, height, u, v, psi;
+   int32_t shape;              /* KGPU_SHAPE_FLAT or KGPU_SHAPE_LEVEL */
+   int32_t _pad;
+} kgpu_cube;
+int kgpu_load_source_conditions(kgpu_handle *h, const kgpu_cap *caps, int32_t ncaps, const kgpu_cube *cubes,
+                                int32_t ncubes, int32_t *num_cells_in_src);
 
 /* ---- multi-GPU (one process per GPU; 2-D block decomposition of the tile grid) */
 

@@ -35,7 +35,8 @@ SWITCHES = {"tanh": 0, "rat3": 1, "cos": 2, "linear": 3, "equal": 4, "0.5": 4, "
 
 
 TOPOG_FUNCS = {"flat": 0, "xslope": 1, "yslope": 2, "xyslope": 3, "xsinslope": 4, "xysinslope": 5, "xhump": 6, "xtanh": 7,
-               "xparab": 8, "xyparab": 9, "xbislope": 10, "x2slopes": 11}
+               "xparab": 8, "xyparab": 9, "xbislope": 10, "x2slopes": 11, "usgs": 12, "flume": 13, "channel power law": 14,
+               "channel_powerlaw": 14, "channel trapezium": 15, "channel_trapezium": 15, "xtrislope": 16}
 
 
 class KgpuSource(C.Structure):

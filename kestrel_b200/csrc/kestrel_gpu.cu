@@ -78,6 +78,7 @@ struct kgpu_handle {
    kgpu_params P;
    DevParams D;
    std::vector<DevSource> src;
+   std::vector<double> srcPool;   // time | flux | psi series of every source (DevSource::off)
    std::string err;
    int dev = 0;
    cudaStream_t stream = nullptr;
@@ -110,7 +111,6 @@ struct kgpu_handle {
    TmaDesc *d_maps = nullptr;  // tensor maps of the state and topography planes (TmaSlot)
    int prefetchDistance = 0;   // L2 prefetch distance of the stage kernel in CTAs (one resident wave)
    int tune = 0;               // StageArgs::tune bits; bit 3 here: 2-D grid without the block list when every block is listed
-   int persistCtas = 444;      // resident CTAs of the stage kernel on this device (3 per SM)
    bool useSpec = true;        // take the (geometric factors, nu == 0) instantiation when the run allows it; KGPU_TUNE bit 6 turns it off
    int nbxAll = 0, nbyAll = 0; // CTA tiles per row / column of the local domain
    int topoBtIdx = -1;         // which bt array the planes were computed from (-1: stale)
@@ -121,6 +121,7 @@ struct kgpu_handle {
    int nBlocks = 0;
    Ctrl *d_ctrl = nullptr, *h_ctrl = nullptr;
    DevSource *d_sources = nullptr;
+   double *d_srcPool = nullptr;
    double *d_stage = nullptr, *h_stage = nullptr;
    size_t stageElems = 0;
    int *d_tileList = nullptr, *d_flags = nullptr, *h_flags = nullptr;
@@ -332,14 +333,13 @@ static void launchStageS(kgpu_handle *h, const StageArgs &a, dim3 grid, bool mm2
 template <bool ONED>
 static void launchStageT(kgpu_handle *h, StageArgs a, int nblocks) {
    if (nblocks <= 0) return;
-   // persistent CTAs: one resident wave (3 CTAs per SM) walks all the tiles, each CTA requesting its next tile's boxes
-   // while it finishes the current one; KGPU_TUNE bit 7 launches one CTA per tile instead (the round-1 schedule)
-   dim3 grid((h->tune & 128) ? nblocks : std::min(nblocks, h->persistCtas));
-   a.nTiles = nblocks;
+   dim3 grid(nblocks);
    a.directNbx = 0;
    a.tune = h->tune & ~8;
-   // every block listed, in row-major order: tile t is block (t % nbx, t / nbx), no list read before the TMA issue
-   if ((h->tune & 8) && a.blockList == h->d_blockList && nblocks == h->nbxAll * h->nbyAll) a.directNbx = h->nbxAll;
+   if ((h->tune & 8) && a.blockList == h->d_blockList && nblocks == h->nbxAll * h->nbyAll && h->nbyAll <= 65535) {
+      a.directNbx = h->nbxAll;
+      grid = dim3(h->nbxAll, h->nbyAll);
+   }
    const bool mm2 = h->P.limiter == KGPU_LIM_MINMOD2;  // the default limiter gets a branch-free instantiation
    // geometric factors on, no eddy viscosity (the reference's defaults): the instantiation with both compiled in
    const bool spec = !ONED && h->useSpec && h->D.geom && !(h->D.nu > 0.0);
@@ -420,7 +420,7 @@ static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int
    a.prefetchDistance = h->prefetchDistance;
    if (h->topoBtIdx != kbt) { int rct = computeTopo(h, kbt); if (rct) return rct; }
    a.tileMask = h->d_tileMask; a.tileSource = h->d_tileSource; a.blockList = h->d_blockList;
-   a.ctrl = h->d_ctrl; a.sources = h->d_sources;
+   a.ctrl = h->d_ctrl; a.sources = h->d_sources; a.sourcePool = h->d_srcPool;
    a.mode = mode;
    a.allActive = h->allActive() ? 1 : 0;
    if (h->timeRhs) cudaEventRecord(h->evA, h->stream);
@@ -634,8 +634,8 @@ static double nextFluxSeriesTime(const kgpu_handle *h, double t) {
    double nextT = HUGE_D, tdiff = HUGE_D;
    for (const DevSource &S : h->src)
       for (int j = 0; j < S.n; j++) {
-         double tmp = S.time[j] - t;
-         if (tmp > 0.0 && tmp < tdiff) { tdiff = tmp; nextT = S.time[j]; }
+         double tmp = h->srcPool[S.off + j] - t;
+         if (tmp > 0.0 && tmp < tdiff) { tdiff = tmp; nextT = h->srcPool[S.off + j]; }
       }
    return nextT;
 }
@@ -802,7 +802,7 @@ int kgpu_destroy(kgpu_handle *h) {
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
    cudaFree(h->d_rankMap);
-   cudaFree(h->d_sources); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
+   cudaFree(h->d_sources); cudaFree(h->d_srcPool); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
    {
       double *pl[15] = {h->topo.b0c, h->topo.bxc, h->topo.byc, h->topo.gamc, h->topo.xb0, h->topo.xB, h->topo.xtan, h->topo.xgam,
@@ -830,7 +830,7 @@ int kgpu_destroy(kgpu_handle *h) {
 
 int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    if (!p || !out || p->struct_bytes != (int32_t)sizeof(kgpu_params)) return KGPU_ERR_ARG;
-   if (p->n_sources > MAX_SOURCES) return KGPU_ERR_UNSUPPORTED;
+   if (p->n_sources < 0 || (p->n_sources > 0 && !p->sources)) return KGPU_ERR_ARG;
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KGPU_ERR_CUDA;  // no CPU fallback
    kgpu_handle *h = new kgpu_handle();
@@ -840,11 +840,14 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    else cudaGetDevice(&h->dev);
    for (int s = 0; s < p->n_sources; s++) {
       const kgpu_source &k = p->sources[s];
-      if (k.n_series > MAX_SERIES || k.n_series < 1) { delete h; return KGPU_ERR_UNSUPPORTED; }
+      if (k.n_series < 1 || !k.time || !k.flux || !k.psi) { delete h; return KGPU_ERR_ARG; }
       DevSource S;
       std::memset(&S, 0, sizeof(S));
       S.x = k.x; S.y = k.y; S.radius = k.radius; S.numCells = k.num_cells_in_src; S.n = k.n_series;
-      for (int j = 0; j < k.n_series; j++) { S.time[j] = k.time[j]; S.flux[j] = k.flux[j]; S.psi[j] = k.psi[j]; }
+      S.off = (long long)h->srcPool.size();
+      h->srcPool.insert(h->srcPool.end(), k.time, k.time + k.n_series);
+      h->srcPool.insert(h->srcPool.end(), k.flux, k.flux + k.n_series);
+      h->srcPool.insert(h->srcPool.end(), k.psi, k.psi + k.n_series);
       h->src.push_back(S);
    }
    h->nX = p->nXpertile; h->nY = p->nYpertile; h->nXt = p->nXtiles; h->nYt = p->nYtiles;
@@ -934,6 +937,8 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    std::memset(h->h_ctrl, 0, sizeof(Ctrl));
    if (cudaMalloc(&h->d_sources, sizeof(DevSource) * std::max<size_t>(1, h->src.size())) != cudaSuccess) return fail("sources");
    if (!h->src.empty()) cudaMemcpyAsync(h->d_sources, h->src.data(), sizeof(DevSource) * h->src.size(), cudaMemcpyHostToDevice, h->stream);
+   if (cudaMalloc(&h->d_srcPool, sizeof(double) * std::max<size_t>(1, h->srcPool.size())) != cudaSuccess) return fail("source series");
+   if (!h->srcPool.empty()) cudaMemcpyAsync(h->d_srcPool, h->srcPool.data(), sizeof(double) * h->srcPool.size(), cudaMemcpyHostToDevice, h->stream);
    size_t ncell = (size_t)h->nX * h->nY, nv = (size_t)(h->nX + 1) * (h->nY + 1);
    h->stageElems = 24 * ncell + 2 * nv;
    if (cudaMalloc(&h->d_stage, h->stageElems * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stageElems * sizeof(double)) != cudaSuccess) return fail("stage");
@@ -962,7 +967,6 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       int nsm = 148;
       if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) nsm = prop.multiProcessorCount;
       h->prefetchDistance = 3 * nsm;
-      h->persistCtas = KGPU_STAGE_MINBLOCKS * nsm;
       if (const char *e = std::getenv("KGPU_PREFETCH_DISTANCE")) h->prefetchDistance = std::atoi(e);  // tuning knob
       h->tune = 31;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0, bit 4 +2.2 %; all five +7.9 %
       if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)
@@ -1066,6 +1070,73 @@ int kgpu_upload_domain(kgpu_handle *h, const double *q4, const double *b0_vertic
    if ((rc = refreshMasks(h))) return rc;
    if ((rc = fillHaloCells(h, h->i0))) return rc;
    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+   return KGPU_OK;
+}
+
+// LoadSourceConditions (SetSources.f90:47-392) on the device: see include/kestrel_gpu.h
+int kgpu_load_source_conditions(kgpu_handle *h, const kgpu_cap *caps, int32_t ncaps, const kgpu_cube *cubes, int32_t ncubes,
+                                int32_t *num_cells_in_src) {
+   if (!h || ncaps < 0 || ncubes < 0 || (ncaps > 0 && !caps) || (ncubes > 0 && !cubes)) return KGPU_ERR_ARG;
+   if (h->comm.active) { h->err = "kgpu_load_source_conditions: single device only (decomposed runs upload their blocks)"; return KGPU_ERR_UNSUPPORTED; }
+   cudaSetDevice(h->dev);
+   const int nsrc = (int)h->src.size();
+   kgpu_cap *dCaps = nullptr;
+   kgpu_cube *dCubes = nullptr;
+   int *dTouch = nullptr, *dCount = nullptr;
+   std::vector<int> touch(h->nTiles), counts(std::max(1, nsrc), 0);
+   auto cleanup = [&]() { cudaFree(dCaps); cudaFree(dCubes); cudaFree(dTouch); cudaFree(dCount); };
+#define LSC_TRY(call)                                                                   \
+   do {                                                                                 \
+      cudaError_t e_ = (call);                                                          \
+      if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return KGPU_ERR_CUDA; } \
+   } while (0)
+   LSC_TRY(cudaMalloc(&dCaps, sizeof(kgpu_cap) * std::max(1, ncaps)));
+   LSC_TRY(cudaMalloc(&dCubes, sizeof(kgpu_cube) * std::max(1, ncubes)));
+   LSC_TRY(cudaMalloc(&dTouch, sizeof(int) * h->nTiles));
+   LSC_TRY(cudaMalloc(&dCount, sizeof(int) * std::max(1, nsrc)));
+   if (ncaps) LSC_TRY(cudaMemcpyAsync(dCaps, caps, sizeof(kgpu_cap) * ncaps, cudaMemcpyHostToDevice, h->stream));
+   if (ncubes) LSC_TRY(cudaMemcpyAsync(dCubes, cubes, sizeof(kgpu_cube) * ncubes, cudaMemcpyHostToDevice, h->stream));
+   LSC_TRY(cudaMemsetAsync(dCount, 0, sizeof(int) * std::max(1, nsrc), h->stream));
+   ShapeTable T{dCaps, dCubes, h->d_sources, ncaps, ncubes, nsrc};
+   // pass 1: which tiles does a shape reach?
+   shape_touch_kernel<<<h->nTiles, 128, 0, h->stream>>>(h->D, T, dTouch);
+   h->launches++;
+   LSC_TRY(cudaMemcpyAsync(touch.data(), dTouch, sizeof(int) * h->nTiles, cudaMemcpyDeviceToHost, h->stream));
+   LSC_TRY(cudaStreamSynchronize(h->stream));
+   // AddTile in the reference's loop order: do i = 1, nXtiles; do j = 1, nYtiles (SetSources.f90:96, 229-231)
+   for (int tx = 0; tx < h->nXt; tx++)
+      for (int ty = 0; ty < h->nYt; ty++) {
+         const int t0 = ty * h->nXt + tx;
+         if (!touch[t0]) continue;
+         int rc = addTile(h, t0, false);
+         if (rc) { cleanup(); return rc; }
+         if (h->tstate[t0] == 2) h->hasSource[t0] = (touch[t0] & 2) ? 1 : 0;   // sponge / dirichlet edge tiles stay off silently
+      }
+   h->masksDirty = true;
+   const int nAct = (int)h->activeList.size();
+   if (nAct > 0) {
+      std::vector<int> tl(nAct);
+      for (int k = 0; k < nAct; k++) tl[k] = h->activeList[k] - 1;
+      LSC_TRY(cudaMemcpyAsync(h->d_tileList, tl.data(), nAct * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      // pass 2: the shapes, cell by cell
+      shape_raster_kernel<<<nAct, 128, 0, h->stream>>>(h->D, T, h->sp(h->i0), h->mp(), h->b0v, h->d_tileList, h->P.TileBuffer, h->d_flags, dCount);
+      h->launches++;
+      LSC_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, nAct * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      LSC_TRY(cudaMemcpyAsync(counts.data(), dCount, sizeof(int) * std::max(1, nsrc), cudaMemcpyDeviceToHost, h->stream));
+      LSC_TRY(cudaStreamSynchronize(h->stream));
+      for (int k = 0; k < nAct; k++) h->seedFlags[tl[k]] = h->h_flags[k];
+   }
+   // NumCellsInSrc (SetSources.f90:372): every cell of the domain counts, and every such cell's tile is active by now
+   for (int s_ = 0; s_ < nsrc; s_++) {
+      h->src[s_].numCells = counts[s_];
+      if (num_cells_in_src) num_cells_in_src[s_] = counts[s_];
+   }
+   if (nsrc) LSC_TRY(cudaMemcpyAsync(h->d_sources, h->src.data(), sizeof(DevSource) * nsrc, cudaMemcpyHostToDevice, h->stream));
+   h->havePre = false;
+   h->firstScan = true;
+   LSC_TRY(cudaStreamSynchronize(h->stream));
+#undef LSC_TRY
+   cleanup();
    return KGPU_OK;
 }
 
@@ -1184,8 +1255,8 @@ int kgpu_output_begin(kgpu_handle *h, double *q4, double *bt_vertices) {
 }
 
 int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams) {
-   if (!h || nparams < 0 || nparams > 8 || (nparams > 0 && !params) || func > KGPU_TOPOG_X2SLOPES) return KGPU_ERR_ARG;
-   static const int need[] = {0, 1, 1, 2, 1, 1, 2, 3, 1, 2, 3, 3};   // parameters each function reads (TopogFuncs.f90)
+   if (!h || nparams < 0 || nparams > 8 || (nparams > 0 && !params) || func > KGPU_TOPOG_XTRISLOPE) return KGPU_ERR_ARG;
+   static const int need[] = {0, 1, 1, 2, 1, 1, 2, 3, 1, 2, 3, 3, 2, 6, 3, 3, 6};   // parameters each function reads (TopogFuncs.f90)
    if (func >= 0 && nparams < need[func]) { h->err = "too few topography parameters"; return KGPU_ERR_ARG; }
    h->topogFn.func = func; h->topogFn.n = nparams;
    for (int k = 0; k < 8; k++) h->topogFn.p[k] = k < nparams ? params[k] : 0.0;

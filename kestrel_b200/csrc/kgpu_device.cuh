@@ -26,16 +26,17 @@ namespace kgpu {
 constexpr int XO = 16;   // x offset of cell 0 in a padded row (doubles)
 constexpr int YO = 2;    // y offset of row 0
 constexpr int HALO = 2;  // cells
-constexpr int MAX_SOURCES = 16;
-constexpr int MAX_SERIES = 16;
 
 // variable slots of the primary state
 enum { QW = 0, QHU = 1, QHV = 2, QHPSI = 3 };
 
+// One flux source (type Sources, RunSettings.f90:101-109).  The time series of ALL sources live in one pool
+// (any number of sources, any series length, as in the reference's allocatable arrays): source J owns
+// pool[off .. off + 3 n): n times, n fluxes, n solids fractions.
 struct DevSource {
    double x, y, radius;
    int numCells, n;
-   double time[MAX_SERIES], flux[MAX_SERIES], psi[MAX_SERIES];
+   long long off;
 };
 
 // Everything a kernel needs that is constant over a run.
@@ -388,30 +389,31 @@ __device__ __forceinline__ double cellY(const DevParams &P, int j) {
 }
 
 // Equations.f90:501-599 -- total volumetric and solids flux of all sources at a cell centre
-__device__ inline void fluxSources(const DevParams &P, const DevSource *src, double tEval, double tGrid, double x, double y,
+__device__ inline void fluxSources(const DevParams &P, const DevSource *src, const double *pool, double tEval, double tGrid, double x, double y,
                                    double &Qt, double &psiQt) {
    double s = 0.0, sp = 0.0;
    for (int J = 0; J < P.nSources; J++) {
       const DevSource &S = src[J];
+      const double *Stime = pool + S.off, *Sflux = Stime + S.n, *Spsi = Sflux + S.n;
       double Qf = 0.0, psiQf = 0.0;
       if (((x - S.x) * (x - S.x) + (y - S.y) * (y - S.y)) < S.radius * S.radius) {
          int n = S.n;
          if (n == 1) {
-            if (tEval < S.time[0] || (tEval == S.time[0] && tGrid < tEval)) {
+            if (tEval < Stime[0] || (tEval == Stime[0] && tGrid < tEval)) {
                Qf = 0.0; psiQf = 0.0;
             } else {
-               Qf = S.flux[0];
-               psiQf = S.psi[0] * Qf;
+               Qf = Sflux[0];
+               psiQf = Spsi[0] * Qf;
             }
          } else {
-            if (tEval < S.time[0] || tEval > S.time[n - 1] || (tEval == S.time[0] && tGrid < tEval) ||
-                (tEval == S.time[n - 1] && tGrid == tEval)) {
+            if (tEval < Stime[0] || tEval > Stime[n - 1] || (tEval == Stime[0] && tGrid < tEval) ||
+                (tEval == Stime[n - 1] && tGrid == tEval)) {
                Qf = 0.0; psiQf = 0.0;
             } else {
                for (int K = 1; K < n; K++) {
-                  if (tEval >= S.time[K - 1] && tEval <= S.time[K]) {
-                     double Qa = S.flux[K - 1], psia = S.psi[K - 1], ta = S.time[K - 1];
-                     double Qb = S.flux[K], psib = S.psi[K], tb = S.time[K];
+                  if (tEval >= Stime[K - 1] && tEval <= Stime[K]) {
+                     double Qa = Sflux[K - 1], psia = Spsi[K - 1], ta = Stime[K - 1];
+                     double Qb = Sflux[K], psib = Spsi[K], tb = Stime[K];
                      Qf = Qa + (Qb - Qa) * (tEval - ta) / (tb - ta);
                      double psif = psia + (psib - psia) * (tEval - ta) / (tb - ta);
                      psiQf = psif * Qf;

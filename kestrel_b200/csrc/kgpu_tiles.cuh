@@ -195,6 +195,118 @@ __global__ void tile_vertices_kernel(const DevParams P, double *vfield, double *
    vfield[g] = stage[k];
 }
 
+// ------------------------------------------------------------------ initial conditions on the device
+// LoadSourceConditions (SetSources.f90:47-392).  Cell coordinates: GridToPhysical (Grid.f90:339-353) = cellX / cellY.
+struct ShapeTable {
+   const kgpu_cap *caps;
+   const kgpu_cube *cubes;
+   const DevSource *src;
+   int ncaps, ncubes, nsrc;
+};
+__device__ __forceinline__ bool capHit(const DevParams &P, const kgpu_cap &c, double x, double y, double &R2) {
+   R2 = P.oneD ? (x - c.x) * (x - c.x) : (x - c.x) * (x - c.x) + (y - c.y) * (y - c.y);
+   return R2 <= c.radius * c.radius;
+}
+__device__ __forceinline__ bool cubeHit(const DevParams &P, const kgpu_cube &c, double x, double y) {
+   return (fabs(x - c.x) <= 0.5 * c.length) && (P.oneD || fabs(y - c.y) <= 0.5 * c.width);
+}
+__device__ __forceinline__ bool sourceHit(const DevParams &P, const DevSource &s, double x, double y) {
+   const double R2 = P.oneD ? (x - s.x) * (x - s.x) : (x - s.x) * (x - s.x) + (y - s.y) * (y - s.y);
+   return R2 <= s.radius * s.radius;   // <= here, strict < in the RHS (quirk Q9)
+}
+// pass 1, one block per tile of the local domain: bit 0 = some cell centre lies in a cap or cube, bit 1 = in a source disc
+__global__ void shape_touch_kernel(const DevParams P, const ShapeTable T, int *touch) {
+   const int t = blockIdx.x, tx = t % P.nXt, ty = t / P.nXt;
+   __shared__ int s_f;
+   if (threadIdx.x == 0) s_f = 0;
+   __syncthreads();
+   int f = 0;
+   for (int k = threadIdx.x; k < P.nX * P.nY; k += blockDim.x) {
+      const int ci = tx * P.nX + k % P.nX, cj = ty * P.nY + k / P.nX;
+      const double x = cellX(P, ci), y = cellY(P, cj);
+      double R2;
+      for (int c = 0; c < T.ncaps; c++) if (capHit(P, T.caps[c], x, y, R2)) f |= 1;
+      for (int c = 0; c < T.ncubes; c++) if (cubeHit(P, T.cubes[c], x, y)) f |= 1;
+      for (int c = 0; c < T.nsrc; c++) if (sourceHit(P, T.src[c], x, y)) f |= 2;
+   }
+   if (f) atomicOr(&s_f, f);
+   __syncthreads();
+   if (threadIdx.x == 0) touch[t] = s_f;
+}
+// pass 2, one block per ACTIVE tile: the shapes cell by cell (the tile's cells start from ActivateTile's state
+// w = b0, everything else 0: UpdateTiles.f90:342-370), NumCellsInSrc, and the seed of the first activation scan
+__global__ void shape_raster_kernel(const DevParams P, const ShapeTable T, StatePtrs S0, MaximaPtrs M, const double *b0v, const int *tiles,
+                                    int buf, int *seedFlags, int *numCells) {
+   const int t = tiles[blockIdx.x], tx = t % P.nXt, ty = t / P.nXt;
+   __shared__ int s_f;
+   if (threadIdx.x == 0) s_f = 0;
+   __syncthreads();
+   int flags = 0;
+   for (int k = threadIdx.x; k < P.nX * P.nY; k += blockDim.x) {
+      const int li = k % P.nX, lj = k / P.nX;
+      const int ci = tx * P.nX + li, cj = ty * P.nY + lj;
+      const size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+      const double x = cellX(P, ci), y = cellY(P, cj);
+      double b0c, btc, bx, by;
+      centreTopoGlobal(P, b0v, (const double *)nullptr, ci, cj, b0c, btc, bx, by);
+      const double gam = gamma2(P, bx, by);
+      double w = b0c, hu = 0.0, hv = 0.0, hpsi = 0.0, Hn = 0.0, Hnmax = 0.0, psimax = 0.0;
+      for (int c = 0; c < T.ncaps; c++) {
+         const kgpu_cap &C = T.caps[c];
+         double R2;
+         if (!capHit(P, C, x, y, R2)) continue;
+         const double rho = P.rhow + (P.rhos - P.rhow) * C.psi;
+         if (C.shape == KGPU_SHAPE_FLAT) {
+            w = w + C.height / gam; Hn = Hn + C.height; Hnmax = Hnmax + C.height;
+            hu = hu + rho * C.height * C.u;
+            if (P.oneD) psimax = psimax + C.psi; else hv = hv + rho * C.height * C.v;
+            hpsi = hpsi + C.psi * C.height;
+         } else if (C.shape == KGPU_SHAPE_PARA) {
+            const double prof = C.height * (1.0 - R2 / C.radius / C.radius);
+            w = w + prof / gam; Hn = Hn + prof; Hnmax = Hnmax + prof;
+            hu = hu + rho * C.height * C.u;          // no parabola factor on the momentum (quirk Q10)
+            if (P.oneD) psimax = psimax + C.psi; else hv = hv + rho * C.height * C.v;
+            hpsi = hpsi + C.psi * C.height * (1.0 - R2 / C.radius / C.radius);
+         } else {   // level: `height` is the free-surface elevation
+            const double hp = C.height - b0c;
+            if (P.oneD) {
+               if (hp > 0.0) {
+                  w = w + hp; Hnmax = Hnmax + hp * gam; Hn = Hn + hp * gam;
+                  hu = hu + rho * hp * gam * C.u; hpsi = hpsi + C.psi * hp * gam; psimax = psimax + C.psi;
+               }
+            } else {
+               const double H = hp * gam;
+               if (H > 0.0) {
+                  w = w + hp; Hn = Hn + H; Hnmax = Hnmax + H;
+                  hu = hu + rho * H * C.u; hv = hv + rho * H * C.v; hpsi = hpsi + C.psi * H;
+               }
+            }
+         }
+      }
+      for (int c = 0; c < T.ncubes; c++) {
+         const kgpu_cube &C = T.cubes[c];
+         if (!cubeHit(P, C, x, y)) continue;
+         if (C.shape == KGPU_SHAPE_LEVEL) {
+            const double hp = C.height - b0c, H = hp * gam;
+            if (H > 0.0) { w = w + hp; Hn = Hn + H; Hnmax = Hnmax + H; hpsi = hpsi + (P.oneD ? C.psi * H : H * C.psi); }
+         } else {
+            w = w + C.height / gam; Hn = Hn + C.height; Hnmax = Hnmax + C.height; hpsi = hpsi + C.psi * C.height;
+         }
+      }
+      for (int c = 0; c < T.nsrc; c++) if (sourceHit(P, T.src[c], x, y)) atomicAdd(&numCells[c], 1);
+      S0.q[QW][g] = w; S0.q[QHU][g] = hu; S0.q[QHV][g] = hv; S0.q[QHPSI][g] = hpsi;
+      M.Hnmax[g] = Hnmax; M.psimax[g] = psimax;
+      if (Hn > P.Hneps) {
+         if (!P.oneD) { if (lj >= P.nY - buf) flags |= 1; if (lj < buf) flags |= 2; }
+         if (li >= P.nX - buf) flags |= 4;
+         if (li < buf) flags |= 8;
+      }
+   }
+   if (flags) atomicOr(&s_f, flags);
+   __syncthreads();
+   if (threadIdx.x == 0) seedFlags[blockIdx.x] = s_f;
+}
+
 // ------------------------------------------------------------------ analytic topography on the device
 // TopogFuncs.f90 evaluated at the vertices of one tile, with the coordinates of Grid.f90:339-353 /
 // UpdateTiles.f90:288-325 (cell centre of local index ii in tile gi: -xSize/2 + dx ((gi-1) nX + ii - 1/2); a vertex
@@ -242,6 +354,38 @@ __global__ void tile_topog_kernel(const DevParams P, const TopogFn F, int gi, in
          double x1 = xc0 - alpha * R / sa, x2 = xc0 - beta * R / sb;
          double arc = zc0 - sqrt(fmax(R * R - (X - xc0) * (X - xc0), 0.0));
          b = X < x1 ? -alpha * X : (X > x2 ? -beta * X : arc);
+         break;
+      }
+      case KGPU_TOPOG_USGS:
+      case KGPU_TOPOG_FLUME: {   // TopogFuncs.f90:145-242
+         double theta0 = 31.0, theta1 = 2.4, xwall = 8.5, wallW = 2.0, wallH = p[0], sigma = p[1];
+         if (F.func == KGPU_TOPOG_FLUME) { theta0 = p[0]; theta1 = p[1]; xwall = p[2]; wallW = p[3]; wallH = p[4]; sigma = p[5]; }
+         double alpha = 8.5 / (asinh(-tan(4.0 * PI / 180.0)) - asinh(-tan(theta0 * PI / 180.0)));
+         double xc0 = -alpha * asinh(-tan(theta0 * PI / 180.0));
+         double zc0 = -alpha * cosh((-xc0) / alpha);
+         double x1 = xc0 + alpha * asinh(-tan(theta1 * PI / 180.0));
+         if (X < 0.0) b = -tan(theta0 * PI / 180.0) * X;
+         else if (X > x1) b = zc0 + alpha * cosh((x1 - xc0) / alpha) - tan(theta1 * PI / 180.0) * (X - x1);
+         else b = zc0 + alpha * cosh((X - xc0) / alpha);
+         if (X < xwall)
+            b = b + 0.5 * wallH * (tanh(sigma * (Y - 0.5 * wallW)) - tanh(sigma * (Y - 1.5 * wallW)) + tanh(sigma * (Y + 1.5 * wallW)) -
+                                   tanh(sigma * (Y + 0.5 * wallW)));
+         break;
+      }
+      case KGPU_TOPOG_CHANNEL_POWERLAW: b = p[0] * X + cos(atan(p[0])) * pow(fabs(Y) / p[1], p[2]); break;                 // :255-276
+      case KGPU_TOPOG_CHANNEL_TRAPEZIUM: b = p[0] * X + cos(atan(p[0])) * fmax(0.0, p[2] * (fabs(Y) - 0.5 * p[1])); break;  // :288-308
+      case KGPU_TOPOG_XTRISLOPE: {   // TopogFuncs.f90:346-388
+         double phi1 = p[0] * PI / 180.0, phi2 = p[1] * PI / 180.0, phi3 = p[2] * PI / 180.0, lam = p[3], x1 = p[4], x2 = p[5];
+         double s1 = tan(phi1), s2 = tan(phi2), s3 = tan(phi3);
+         double c2 = (x1 - 0.5 * lam) * 0.5 * (s1 - s2);
+         double c3 = (x1 + 0.5 * lam) * 0.5 * (s1 - s2) + c2;
+         double c4 = (x2 - 0.5 * lam) * 0.5 * (s2 - s3) + c3;
+         double c5 = (x2 + 0.5 * lam) * 0.5 * (s2 - s3) + c4;
+         if (X < x1 - 0.5 * lam) b = s1 * X;
+         else if (X < x1 + 0.5 * lam) { double A = 0.5 * (s2 - s1) * lam / PI; b = A * sin((X - x1) * PI / lam - 0.5 * PI) + 0.5 * (s1 + s2) * X + c2; }
+         else if (X < x2 - 0.5 * lam) b = s2 * X + c3;
+         else if (X < x2 + 0.5 * lam) { double A = 0.5 * (s3 - s2) * lam / PI; b = A * sin((X - x2) * PI / lam - 0.5 * PI) + 0.5 * (s2 + s3) * X + c4; }
+         else b = s3 * X + c5;
          break;
       }
       default: break;

@@ -72,8 +72,46 @@ def topog(rs, xv: np.ndarray, yv: np.ndarray) -> np.ndarray:
         x2 = xc0 - beta * R / sb
         arc = zc0 - np.sqrt(np.maximum(R * R - (X - xc0) * (X - xc0), 0.0))
         return np.where(X < x1, -alpha * X, np.where(X > x2, -beta * X, arc))
-    raise ValueError(f"topography function '{rs.topog_func}' is not available "
-                     "(usgs, flume, channel_*, xtrislope and raster DEMs are out of scope)")
+    if name in ("usgs", "flume"):  # TopogFuncs.f90:145-242: two slopes joined by a cosh arc, tanh side walls
+        if name == "usgs":
+            theta0, theta1, xwall, wallW, wallH, sigma = 31.0, 2.4, 8.5, 2.0, p[0], p[1]
+        else:
+            theta0, theta1, xwall, wallW, wallH, sigma = p[0], p[1], p[2], p[3], p[4], p[5]
+        alpha = 8.5 / (math.asinh(-math.tan(4.0 * PI / 180.0)) - math.asinh(-math.tan(theta0 * PI / 180.0)))
+        xc0 = -alpha * math.asinh(-math.tan(theta0 * PI / 180.0))
+        zc0 = -alpha * math.cosh((-xc0) / alpha)
+        x1 = xc0 + alpha * math.asinh(-math.tan(theta1 * PI / 180.0))
+        up = -math.tan(theta0 * PI / 180.0) * X
+        down = zc0 + alpha * math.cosh((x1 - xc0) / alpha) - math.tan(theta1 * PI / 180.0) * (X - x1)
+        with np.errstate(over="ignore"):
+            arc = zc0 + alpha * np.cosh((X - xc0) / alpha)
+        b = np.where(X < 0.0, up, np.where(X > x1, down, arc))
+        walls = 0.5 * wallH * (np.tanh(sigma * (Y - 0.5 * wallW)) - np.tanh(sigma * (Y - 1.5 * wallW))
+                               + np.tanh(sigma * (Y + 1.5 * wallW)) - np.tanh(sigma * (Y + 0.5 * wallW)))
+        return np.where(X < xwall, b + walls, b)
+    if name in ("channel power law", "channel_powerlaw"):  # TopogFuncs.f90:255-276
+        slope, W, alpha = p[0], p[1], p[2]
+        costheta = math.cos(math.atan(slope))
+        return slope * X + costheta * (np.abs(Y) / W) ** alpha
+    if name in ("channel trapezium", "channel_trapezium"):  # TopogFuncs.f90:288-308
+        slope, W, Sb = p[0], p[1], p[2]
+        costheta = math.cos(math.atan(slope))
+        return slope * X + costheta * np.maximum(0.0, Sb * (np.abs(Y) - 0.5 * W))
+    if name == "xtrislope":  # TopogFuncs.f90:346-388
+        phi1, phi2, phi3 = p[0] * PI / 180.0, p[1] * PI / 180.0, p[2] * PI / 180.0
+        lam, x1, x2 = p[3], p[4], p[5]
+        s1, s2, s3 = math.tan(phi1), math.tan(phi2), math.tan(phi3)
+        c2 = (x1 - 0.5 * lam) * 0.5 * (s1 - s2)
+        c3 = (x1 + 0.5 * lam) * 0.5 * (s1 - s2) + c2
+        c4 = (x2 - 0.5 * lam) * 0.5 * (s2 - s3) + c3
+        c5 = (x2 + 0.5 * lam) * 0.5 * (s2 - s3) + c4
+        A12, A23 = 0.5 * (s2 - s1) * lam / PI, 0.5 * (s3 - s2) * lam / PI
+        return np.where(X < x1 - 0.5 * lam, s1 * X,
+               np.where(X < x1 + 0.5 * lam, A12 * np.sin((X - x1) * PI / lam - 0.5 * PI) + 0.5 * (s1 + s2) * X + c2,
+               np.where(X < x2 - 0.5 * lam, s2 * X + c3,
+               np.where(X < x2 + 0.5 * lam, A23 * np.sin((X - x2) * PI / lam - 0.5 * PI) + 0.5 * (s2 + s3) * X + c4,
+                        s3 * X + c5))))
+    raise ValueError(f"topography function '{rs.topog_func}' is not available (raster DEMs are out of scope)")
 
 
 def tile_heights(rs, tile_id: int) -> np.ndarray:

@@ -352,6 +352,47 @@ double TopogFunction(const RunSet &rs, double X, double Y) {  // TopogFuncs.f90
       double a1 = std::tan(phi1), a2 = std::tan(phi2);
       return -0.5 * (a1 + a2) * X + 0.5 * (a1 - a2) * lam * std::log(std::cosh(X / lam));
    }
+   if (name == "usgs" || name == "flume") {  // TopogFuncs.f90:145-242: two slopes joined by a cosh arc, tanh side walls
+      double theta0 = 31.0, theta1 = 2.4, xwall = 8.5, wallW = 2.0, wallH, sigma;
+      if (name == "usgs") { need(2); wallH = p[0]; sigma = p[1]; }
+      else { need(6); theta0 = p[0]; theta1 = p[1]; xwall = p[2]; wallW = p[3]; wallH = p[4]; sigma = p[5]; }
+      double alpha = 8.5 / (std::asinh(-std::tan(4.0 * PI / 180.0)) - std::asinh(-std::tan(theta0 * PI / 180.0)));
+      double xc0 = -alpha * std::asinh(-std::tan(theta0 * PI / 180.0));
+      double zc0 = -alpha * std::cosh((-xc0) / alpha);
+      double x1 = xc0 + alpha * std::asinh(-std::tan(theta1 * PI / 180.0));
+      double b;
+      if (X < 0.0) b = -std::tan(theta0 * PI / 180.0) * X;
+      else if (X > x1) b = zc0 + alpha * std::cosh((x1 - xc0) / alpha) - std::tan(theta1 * PI / 180.0) * (X - x1);
+      else b = zc0 + alpha * std::cosh((X - xc0) / alpha);
+      if (X < xwall)
+         b = b + 0.5 * wallH * (std::tanh(sigma * (Y - 0.5 * wallW)) - std::tanh(sigma * (Y - 1.5 * wallW)) +
+                                std::tanh(sigma * (Y + 1.5 * wallW)) - std::tanh(sigma * (Y + 0.5 * wallW)));
+      return b;
+   }
+   if (name == "channel power law" || name == "channel_powerlaw") {  // TopogFuncs.f90:255-276
+      need(3);
+      double costheta = std::cos(std::atan(p[0]));
+      return p[0] * X + costheta * std::pow(std::fabs(Y) / p[1], p[2]);
+   }
+   if (name == "channel trapezium" || name == "channel_trapezium") {  // TopogFuncs.f90:288-308
+      need(3);
+      double costheta = std::cos(std::atan(p[0]));
+      return p[0] * X + costheta * std::max(0.0, p[2] * (std::fabs(Y) - 0.5 * p[1]));
+   }
+   if (name == "xtrislope") {  // TopogFuncs.f90:346-388
+      need(6);
+      double phi1 = p[0] * PI / 180.0, phi2 = p[1] * PI / 180.0, phi3 = p[2] * PI / 180.0, lam = p[3], x1 = p[4], x2 = p[5];
+      double s1 = std::tan(phi1), s2 = std::tan(phi2), s3 = std::tan(phi3);
+      double c2 = (x1 - 0.5 * lam) * 0.5 * (s1 - s2);
+      double c3 = (x1 + 0.5 * lam) * 0.5 * (s1 - s2) + c2;
+      double c4 = (x2 - 0.5 * lam) * 0.5 * (s2 - s3) + c3;
+      double c5 = (x2 + 0.5 * lam) * 0.5 * (s2 - s3) + c4;
+      if (X < x1 - 0.5 * lam) return s1 * X;
+      if (X < x1 + 0.5 * lam) { double A = 0.5 * (s2 - s1) * lam / PI; return A * std::sin((X - x1) * PI / lam - 0.5 * PI) + 0.5 * (s1 + s2) * X + c2; }
+      if (X < x2 - 0.5 * lam) return s2 * X + c3;
+      if (X < x2 + 0.5 * lam) { double A = 0.5 * (s3 - s2) * lam / PI; return A * std::sin((X - x2) * PI / lam - 0.5 * PI) + 0.5 * (s2 + s3) * X + c4; }
+      return s3 * X + c5;
+   }
    if (name == "x2slopes") {
       need(3);
       double alpha = p[0], beta = p[1], R = p[2];
@@ -669,9 +710,9 @@ Simulation::Simulation(RunSet rs) : rs_(std::move(rs)) {
    // (kgpu_set_topography_function) instead of from the callback above; functions the library does not know keep the callback
    if (const char *e = std::getenv("KESTREL_GPU_DEVICE_TOPOGRAPHY")) {
       static const char *names[] = {"flat", "xslope", "yslope", "xyslope", "xsinslope", "xysinslope", "xhump", "xtanh", "xparab", "xyparab",
-                                    "xbislope", "x2slopes"};
+                                    "xbislope", "x2slopes", "usgs", "flume", "channel power law", "channel trapezium", "xtrislope"};
       if (e[0] == '1' && rs_.topog_type == "function")
-         for (int f = 0; f < 12; f++)
+         for (int f = 0; f < 17; f++)
             if (rs_.topog_func == names[f]) {
                Check(kgpu_set_topography_function(h_, f, rs_.topog_params.data(), (int32_t)rs_.topog_params.size()), "kgpu_set_topography_function");
                break;

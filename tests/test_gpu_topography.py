@@ -41,7 +41,8 @@ def test_dynamic_tiles_with_device_topography_are_bit_identical(gpu_lib, case, k
 @pytest.mark.parametrize("func,params", [
     ("flat", []), ("xslope", [-0.04]), ("yslope", [0.03]), ("xyslope", [-0.08, 0.03]), ("xsinslope", [0.3]), ("xysinslope", [0.2]),
     ("xhump", [0.5, 9.0]), ("xtanh", [2.0, 0.4, 5.0]), ("xparab", [0.002]), ("xyparab", [0.002, 0.001]), ("xbislope", [20.0, 5.0, 3.0]),
-    ("x2slopes", [0.5, 0.1, 12.0]),
+    ("x2slopes", [0.5, 0.1, 12.0]), ("usgs", [0.3, 4.0]), ("flume", [28.0, 3.0, 6.0, 1.5, 0.4, 3.0]),
+    ("channel power law", [-0.05, 4.0, 2.5]), ("channel trapezium", [-0.05, 5.0, 0.8]), ("xtrislope", [25.0, 10.0, 2.0, 4.0, -6.0, 5.0]),
 ])
 def test_every_topography_function_matches_the_host(gpu_lib, func, params):
     """Heights of a freshly activated tile: device kernel against kestrel_b200/host/topog.py (TopogFuncs.f90)."""
@@ -55,7 +56,7 @@ def test_every_topography_function_matches_the_host(gpu_lib, func, params):
     st.upload_tile(tid, u, b0v=None)          # no heights given: the library evaluates them
     got = st.download_tile(tid)["b0"]
     ref = tile_heights(rs, tid)
-    algebraic = func in ("flat", "xslope", "yslope", "xyslope", "xparab", "xyparab")
+    algebraic = func in ("flat", "xslope", "yslope", "xyslope", "xparab", "xyparab")   # no libm call at all
     tol = 32 * 2.2e-16 * max(1.0, float(np.max(np.abs(ref))))
     assert np.max(np.abs(got - ref)) <= tol
     if algebraic:
