@@ -57,6 +57,19 @@ module kestrel_gpu
       type(c_ptr) :: psi
    end type kgpu_source
 
+   ! ---- struct kgpu_cap / kgpu_cube: types Caps and Cubes (src/RunSettings.f90:56-88) for kgpu_load_source_conditions
+   integer(c_int32_t), parameter :: KGPU_SHAPE_FLAT = 0, KGPU_SHAPE_PARA = 1, KGPU_SHAPE_LEVEL = 2
+   type, bind(C) :: kgpu_cap
+      real(c_double) :: x, y, radius, height, u, v, psi
+      integer(c_int32_t) :: shape
+      integer(c_int32_t) :: pad
+   end type kgpu_cap
+   type, bind(C) :: kgpu_cube
+      real(c_double) :: x, y, length, width, height, u, v, psi
+      integer(c_int32_t) :: shape
+      integer(c_int32_t) :: pad
+   end type kgpu_cube
+
    ! ---- struct kgpu_params: the RunSet fields the path reads (src/RunSettings.f90:161-340)
    type, bind(C) :: kgpu_params
       integer(c_int32_t) :: struct_bytes
@@ -241,6 +254,38 @@ module kestrel_gpu
          integer(c_int32_t), value :: nparams
          integer(c_int) :: rc
       end function kgpu_set_topography_function
+
+      ! int kgpu_set_topography_raster(kgpu_handle *h, const double *elev, int32_t nx, int32_t ny, double origin_x,
+      !                                double origin_y, double pixel_w, double pixel_h, double centre_e, double centre_n);
+      function kgpu_set_topography_raster(h, elev, nx, ny, origin_x, origin_y, pixel_w, pixel_h, centre_e, centre_n) &
+            bind(C, name="kgpu_set_topography_raster") result(rc)
+         import :: c_int, c_int32_t, c_double, c_ptr
+         type(c_ptr), value :: h
+         type(c_ptr), value :: elev
+         integer(c_int32_t), value :: nx
+         integer(c_int32_t), value :: ny
+         real(c_double), value :: origin_x
+         real(c_double), value :: origin_y
+         real(c_double), value :: pixel_w
+         real(c_double), value :: pixel_h
+         real(c_double), value :: centre_e
+         real(c_double), value :: centre_n
+         integer(c_int) :: rc
+      end function kgpu_set_topography_raster
+
+      ! int kgpu_load_source_conditions(kgpu_handle *h, const kgpu_cap *caps, int32_t ncaps, const kgpu_cube *cubes,
+      !                                 int32_t ncubes, int32_t *num_cells_in_src);
+      function kgpu_load_source_conditions(h, caps, ncaps, cubes, ncubes, num_cells_in_src) &
+            bind(C, name="kgpu_load_source_conditions") result(rc)
+         import :: c_int, c_int32_t, c_ptr
+         type(c_ptr), value :: h
+         type(c_ptr), value :: caps
+         integer(c_int32_t), value :: ncaps
+         type(c_ptr), value :: cubes
+         integer(c_int32_t), value :: ncubes
+         type(c_ptr), value :: num_cells_in_src
+         integer(c_int) :: rc
+      end function kgpu_load_source_conditions
 
       ! int kgpu_comm_id_bytes(void);
       function kgpu_comm_id_bytes() bind(C, name="kgpu_comm_id_bytes") result(nbytes)

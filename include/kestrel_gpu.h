@@ -229,6 +229,18 @@ enum { KGPU_TOPOG_FLAT = 0, KGPU_TOPOG_XSLOPE, KGPU_TOPOG_YSLOPE, KGPU_TOPOG_XYS
        KGPU_TOPOG_CHANNEL_TRAPEZIUM, KGPU_TOPOG_XTRISLOPE };
 int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *params, int32_t nparams);
 
+/* ---- DEM ingest on the device -----------------------------------
+ * For raster topographies (`Topog Type = DEM / raster / SRTM`) the host keeps GDAL: it reads the raster section that
+ * covers the domain once (GetRasterData, src/dem.f90:193-257) and hands it over; the library then resamples the heights
+ * of every tile it activates itself -- TileHeightData (src/dem.f90:260-356): the mean of four bicubic interpolations
+ * (Bicubic_r, src/Interp2d.f90:214-292) at the vertex +- half a cell -- instead of calling the heights callback per tile.
+ *   elev      : nx * ny pixel values, x fastest: Elev(i, j) of GetRasterData, nodata already replaced
+ *   origin_*, pixel_* : rOX, rOY, rdX, rdY of that section (pixel_h is negative for north-up rasters)
+ *   centre_e, centre_n: RunParams%centerUTM
+ * Copies the raster to the device; func < 0 of kgpu_set_topography_function returns to the callback. */
+int kgpu_set_topography_raster(kgpu_handle *h, const double *elev, int32_t nx, int32_t ny, double origin_x, double origin_y,
+                               double pixel_w, double pixel_h, double centre_e, double centre_n);
+
 /* ---- initial conditions on the device ------------------------
  * LoadSourceConditions (src/SetSources.f90:47-392) inside the library: the caps and cubes of the input file are
  * rasterised on the device instead of on the host followed by one kgpu_upload_tile per tile.  Every tile with a

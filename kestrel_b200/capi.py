@@ -47,6 +47,17 @@ class KgpuSource(C.Structure):
     ]
 
 
+class KgpuCap(C.Structure):   # kgpu_cap
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("radius", C.c_double), ("height", C.c_double), ("u", C.c_double),
+                ("v", C.c_double), ("psi", C.c_double), ("shape", C.c_int32), ("_pad", C.c_int32)]
+
+
+class KgpuCube(C.Structure):  # kgpu_cube
+    _fields_ = [("x", C.c_double), ("y", C.c_double), ("length", C.c_double), ("width", C.c_double), ("height", C.c_double),
+                ("u", C.c_double), ("v", C.c_double), ("psi", C.c_double), ("shape", C.c_int32), ("_pad", C.c_int32)]
+
+
+SHAPES = {"flat": 0, "para": 1, "level": 2}
 HEIGHTS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_double))
 
 
@@ -145,6 +156,9 @@ class Library:
             ("output_begin", C.c_int, [C.c_void_p, _dp, _dp]),
             ("output_wait", C.c_int, [C.c_void_p]),
             ("morpho_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+            ("set_topography_raster", C.c_int, [C.c_void_p, _dp, C.c_int32, C.c_int32] + [C.c_double] * 6),
+            ("load_source_conditions", C.c_int, [C.c_void_p, C.POINTER(KgpuCap), C.c_int32, C.POINTER(KgpuCube), C.c_int32,
+                                                 C.POINTER(C.c_int32)]),
             ("debug_sequential_walk", C.c_int, [C.c_void_p, C.c_int32]),
             ("debug_global_walk", C.c_int, [C.c_void_p, C.c_int32]),
             ("debug_redist_capacity", C.c_int, [C.c_void_p, C.c_int32]),
@@ -271,6 +285,14 @@ class Stepper:
         arr = np.ascontiguousarray(list(params), dtype=np.float64)
         self._check(self.lib.set_topography_function(self.h, func, _ptr(arr) if arr.size else None, int(arr.size)))
 
+    def set_topography_raster(self, elev: np.ndarray, origin_x: float, origin_y: float, pixel_w: float, pixel_h: float,
+                              centre_e: float = 0.0, centre_n: float = 0.0):
+        """Resample the heights of every tile activated from now on from this raster section on the device
+        (TileHeightData, dem.f90:260-356).  elev[j, i] = Elev(i + 1, j + 1): x fastest."""
+        elev = np.ascontiguousarray(elev, dtype=np.float64)
+        ny, nx = elev.shape
+        self._check(self.lib.set_topography_raster(self.h, _ptr(elev), nx, ny, origin_x, origin_y, pixel_w, pixel_h, centre_e, centre_n))
+
     def output_begin(self, q4: np.ndarray, btv: Optional[np.ndarray] = None):
         """Asynchronous output gather: device snapshot now, transfer into q4 (and btv) while the next
         kgpu_integrate_to calls run.  The arrays must stay alive and untouched until output_wait()."""
@@ -279,6 +301,19 @@ class Stepper:
 
     def output_wait(self):
         self._check(self.lib.output_wait(self.h))
+
+    def load_source_conditions(self, caps: Sequence = (), cubes: Sequence = (), n_sources: int = 0):
+        """LoadSourceConditions on the device (kgpu_load_source_conditions): caps / cubes are the host dataclasses of
+        kestrel_b200.host.settings.  Returns NumCellsInSrc of the handle's flux sources."""
+        ca = (KgpuCap * max(1, len(caps)))()
+        for k, c in enumerate(caps):
+            ca[k] = KgpuCap(c.x, c.y, c.radius, c.height, c.u, c.v, c.psi, SHAPES[c.shape], 0)
+        cu = (KgpuCube * max(1, len(cubes)))()
+        for k, c in enumerate(cubes):
+            cu[k] = KgpuCube(c.x, c.y, c.length, c.width, c.height, c.u, c.v, c.psi, SHAPES[c.shape], 0)
+        counts = (C.c_int32 * max(1, n_sources))()
+        self._check(self.lib.load_source_conditions(self.h, ca, len(caps), cu, len(cubes), counts))
+        return [int(counts[k]) for k in range(n_sources)]
 
     def morpho_stats(self):
         """(cells handed to RedistributeGrid, enlargements of its list buffer) since creation."""

@@ -154,6 +154,8 @@ struct kgpu_handle {
    bool outputPending = false;
    RedistGlobalBufs rg;
    TopogFn topogFn = {-1, 0, {0, 0, 0, 0, 0, 0, 0, 0}};   // analytic topography evaluated on the device (func < 0: heights callback)
+   RasterDesc raster = {nullptr, 0, 0, 0, 0, 0, 0, 0, 0};  // DEM section resampled on the device (elev == nullptr: not set)
+   double *d_raster = nullptr;
 
    bool allActive() const { return (int)activeList.size() == nTiles; }
    StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
@@ -487,7 +489,8 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
    int nX = h->nX, nY = h->nY;
    size_t nv = (size_t)(nX + 1) * (nY + 1);
    double *hb = h->h_stage;
-   const bool onDevice = !given && h->topogFn.func >= 0;
+   const bool fromRaster = !given && h->raster.elev != nullptr;
+   const bool onDevice = !given && (fromRaster || h->topogFn.func >= 0);
    if (given) {
       std::memcpy(hb, given, sizeof(double) * (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1));
    } else if (!onDevice) {
@@ -504,7 +507,8 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
    int tx, ty; tileXY(h, t0, tx, ty);
    dim3 grid((nX + 1 + 127) / 128, h->oneD ? 1 : nY + 1);
    if (onDevice) {   // TopogFuncs.f90 at the tile's vertices, straight into the staging buffer (global 1-based tile indices)
-      tile_topog_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->topogFn, h->gtx0 + tx + 1, h->gty0 + ty + 1, h->d_stage);
+      if (fromRaster) tile_raster_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->raster, h->gtx0 + tx + 1, h->gty0 + ty + 1, h->d_stage);
+      else tile_topog_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->topogFn, h->gtx0 + tx + 1, h->gty0 + ty + 1, h->d_stage);
       h->launches++;
    } else CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, hb, nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
    tile_vertices_kernel<<<grid, 128, 0, h->stream>>>(h->D, h->b0v, h->d_stage, tx, ty, 1, mask);
@@ -801,7 +805,7 @@ int kgpu_destroy(kgpu_handle *h) {
    cudaFree(h->I0); cudaFree(h->b0v); cudaFree(h->EBt); cudaFree(h->EmD);
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
-   cudaFree(h->d_rankMap);
+   cudaFree(h->d_rankMap); cudaFree(h->d_raster);
    cudaFree(h->d_sources); cudaFree(h->d_srcPool); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
    cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
    {
@@ -1260,6 +1264,18 @@ int kgpu_set_topography_function(kgpu_handle *h, int32_t func, const double *par
    if (func >= 0 && nparams < need[func]) { h->err = "too few topography parameters"; return KGPU_ERR_ARG; }
    h->topogFn.func = func; h->topogFn.n = nparams;
    for (int k = 0; k < 8; k++) h->topogFn.p[k] = k < nparams ? params[k] : 0.0;
+   return KGPU_OK;
+}
+
+int kgpu_set_topography_raster(kgpu_handle *h, const double *elev, int32_t nx, int32_t ny, double origin_x, double origin_y,
+                               double pixel_w, double pixel_h, double centre_e, double centre_n) {
+   if (!h || !elev || nx < 2 || ny < 2 || pixel_w == 0.0 || pixel_h == 0.0) return KGPU_ERR_ARG;
+   cudaSetDevice(h->dev);
+   cudaFree(h->d_raster);
+   h->d_raster = nullptr; h->raster.elev = nullptr;
+   CUDA_TRY(h, cudaMalloc(&h->d_raster, sizeof(double) * (size_t)nx * ny));
+   CUDA_TRY(h, cudaMemcpy(h->d_raster, elev, sizeof(double) * (size_t)nx * ny, cudaMemcpyHostToDevice));
+   h->raster = RasterDesc{h->d_raster, nx, ny, origin_x, origin_y, pixel_w, pixel_h, centre_e, centre_n};
    return KGPU_OK;
 }
 

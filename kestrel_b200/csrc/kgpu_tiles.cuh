@@ -195,6 +195,91 @@ __global__ void tile_vertices_kernel(const DevParams P, double *vfield, double *
    vfield[g] = stage[k];
 }
 
+// ------------------------------------------------------------------ DEM ingest on the device
+// TileHeightData (dem.f90:260-356): the height of a tile vertex is the mean of four bicubic interpolations of the
+// raster at the vertex +- half a cell in x and y; Bicubic_r (Interp2d.f90:214-292) builds the 16 coefficients of the
+// bicubic patch from the values and centred finite differences at the four pixels around the point with the constant
+// matrix m (Interp2d.f90:57-74) and evaluates it in Horner form.  The raster is held on the device as Elev(i, j),
+// i fastest, 1-based pixel indices as in the reference; image coordinates imgx = (E - originX) / pixelW + 1.
+// (The reference reads one raster section per tile through GDAL; here the library holds the section that covers the
+// domain and every tile indexes into it.  Stencil indices are clamped to the raster.)
+struct RasterDesc {
+   const double *elev;
+   int nx, ny;
+   double originX, originY, pixelW, pixelH, centreE, centreN;
+};
+__constant__ double c_bicubicM[256] = {
+   1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+   0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0,
+   -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0,
+   2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0,
+   0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+   0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0,
+   0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0,
+   0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0,
+   -3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+   0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0,
+   9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1,
+   -6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1,
+   2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+   0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0,
+   -6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1,
+   4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1};
+__device__ inline double bicubicR(const RasterDesc &R, double x, double y) {
+   const int x0 = (int)floor(x), x1 = (int)ceil(x), y0 = (int)floor(y), y1 = (int)ceil(y);
+   auto z = [&](int i, int j) -> double {
+      i = i < 1 ? 1 : (i > R.nx ? R.nx : i);
+      j = j < 1 ? 1 : (j > R.ny ? R.ny : j);
+      return R.elev[(size_t)(j - 1) * R.nx + (i - 1)];
+   };
+   double f[16];
+   const double dx0 = (double)(x1 - x0 + 1), dx1 = (double)(x1 + 1 - x0), dy0 = (double)(y1 - y0 + 1), dy1 = (double)(y1 + 1 - y0);
+   f[0] = z(x0, y0); f[1] = z(x1, y0); f[2] = z(x0, y1); f[3] = z(x1, y1);
+   f[4] = (z(x1, y0) - z(x0 - 1, y0)) / dx0;
+   f[5] = (z(x1 + 1, y0) - z(x0, y0)) / dx1;
+   f[6] = (z(x1, y1) - z(x0 - 1, y1)) / dx0;
+   f[7] = (z(x1 + 1, y1) - z(x0, y1)) / dx1;
+   f[8] = (z(x0, y1) - z(x0, y0 - 1)) / dy0;
+   f[9] = (z(x1, y1) - z(x1, y0 - 1)) / dy0;
+   f[10] = (z(x0, y1 + 1) - z(x0, y0)) / dy1;
+   f[11] = (z(x1, y1 + 1) - z(x1, y0)) / dy1;
+   f[12] = ((z(x1, y1) - z(x0 - 1, y1)) - (z(x1, y0 - 1) - z(x0 - 1, y0 - 1))) / dx0 / dy0;
+   f[13] = ((z(x1 + 1, y1) - z(x0, y1)) - (z(x1 + 1, y0 - 1) - z(x0, y0 - 1))) / dx1 / dy0;
+   f[14] = ((z(x1, y1 + 1) - z(x0 - 1, y1 + 1)) - (z(x1, y0) - z(x0 - 1, y0))) / dx0 / dy1;
+   f[15] = ((z(x1 + 1, y1 + 1) - z(x0, y1 + 1)) - (z(x1 + 1, y0) - z(x0, y0))) / dx1 / dy1;
+   double a[16];   // aVec = matmul(m, fVec); a(i, j) = aVec(4 (i - 1) + j)
+   for (int r = 0; r < 16; r++) {
+      double acc = 0.0;
+      for (int c = 0; c < 16; c++) acc = acc + c_bicubicM[r * 16 + c] * f[c];
+      a[r] = acc;
+   }
+   const double t = (x == (double)x0) ? 0.0 : (x - (double)x0) / (double)(x1 - x0);
+   const double u = (y == (double)y0) ? 0.0 : (y - (double)y0) / (double)(y1 - y0);
+   double ans = 0.0;
+   for (int i = 3; i >= 0; i--) ans = t * ans + ((a[i * 4 + 3] * u + a[i * 4 + 2]) * u + a[i * 4 + 1]) * u + a[i * 4 + 0];
+   return ans;
+}
+// heights of one tile's vertices from the raster, into the staging buffer (same layout as tile_topog_kernel's)
+__global__ void tile_raster_kernel(const DevParams P, const RasterDesc R, int gi, int gj, double *stage) {
+   int li = blockIdx.x * blockDim.x + threadIdx.x;
+   int lj = blockIdx.y;
+   int nvy = P.oneD ? 1 : P.nY + 1;
+   if (li > P.nX || lj >= nvy) return;
+   auto xc = [&](int ii) { return -0.5 * P.xSize + P.dx * ((gi - 1.0) * P.nX + (ii - 0.5)); };
+   auto yc = [&](int jj) { return -0.5 * P.ySize + P.dy * ((gj - 1.0) * P.nY + (jj - 0.5)); };
+   const double X = li < P.nX ? xc(li + 1) - 0.5 * P.dx : xc(P.nX) + 0.5 * P.dx;   // x_vertex, y_vertex (UpdateTiles.f90:288-325)
+   const double Y = lj < P.nY ? yc(lj + 1) - 0.5 * P.dy : yc(P.nY) + 0.5 * P.dy;
+   double s = 0.0;   // 0.25 * sum(hcorner), hcorner(k), k = jj + 2 (ii - 1)
+   for (int ii = 1; ii <= 2; ii++)
+      for (int jj = 1; jj <= 2; jj++) {
+         const double E = R.centreE + X + ((double)(ii - 1) - 0.5) * P.dx;
+         const double N = R.centreN + Y + ((double)(jj - 1) - 0.5) * P.dy;
+         const double imgx = (E - R.originX) / R.pixelW + 1, imgy = (N - R.originY) / R.pixelH + 1;
+         s = s + bicubicR(R, imgx, imgy);
+      }
+   stage[(size_t)lj * (P.nX + 1) + li] = 0.25 * s;
+}
+
 // ------------------------------------------------------------------ initial conditions on the device
 // LoadSourceConditions (SetSources.f90:47-392).  Cell coordinates: GridToPhysical (Grid.f90:339-353) = cellX / cellY.
 struct ShapeTable {

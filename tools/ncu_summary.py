@@ -14,7 +14,10 @@ rep, cells, out = sys.argv[1], float(sys.argv[2]), sys.argv[3]
 note = sys.argv[4] if len(sys.argv) > 4 else ""
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, val = rows[0], rows[1], rows[-1]
+# a report with several captured launches has one value row per launch: KERNEL_INDEX (env, default: the last) picks one
+import os
+_ki = os.environ.get("KERNEL_INDEX")
+hdr, units, val = rows[0], rows[1], (rows[2 + int(_ki)] if _ki is not None else rows[-1])
 get = lambda k: (val[hdr.index(k)], units[hdr.index(k)]) if k in hdr else None
 keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
@@ -33,9 +36,15 @@ for i, h in enumerate(hdr):
         stalls[h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = float(val[i])
 summ["stall_cycles_per_issued_instruction"] = dict(sorted(stalls.items(), key=lambda x: -x[1])[:10])
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout.splitlines()
-start = next(i for i, l in enumerate(src) if l.startswith('"Address"'))
+starts = [i for i, l in enumerate(src) if l.startswith('"Address"')]
+start = starts[int(_ki)] if _ki is not None else starts[-1]
+stop = len(src)
+for j in range(start + 1, len(src)):
+    if not src[j].startswith('"0x'):
+        stop = j
+        break
 ops = collections.Counter()
-for r in csv.DictReader(io.StringIO("\n".join(src[start:]))):
+for r in csv.DictReader(io.StringIO("\n".join(src[start:stop]))):
     t = r["Source"].split()
     if not t:
         continue
