@@ -372,7 +372,8 @@ def main():
         pk = props.multi_processor_count * 4 * 0.5 * mhz * 1e6
         ach = per * cells / (k_ms * 1e-3)
         fp64 = {"achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": pk, "frac": ach / pk, "warp_inst_per_cell": per,
-                "note": "the pipe that binds first for this scheme (DESIGN.md section 5); peak = SMs x 4 x 0.5 per cycle at the sampled SM clock"}
+                "note": "second roofline (DESIGN.md section 5); peak = SMs x 4 x 0.5 warp-instructions per cycle at the sampled SM clock -- "
+                        "measured on this pool's B200: 63.2 DFMA / clk / SM (tools/microbench/fp64_peak.cu, profiles/r02_fp64_peak.json)"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "fp64_pipe": fp64,

