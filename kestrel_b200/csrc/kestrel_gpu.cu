@@ -696,18 +696,11 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    ctrl_check_kernel<<<1, 1, 0, h->stream>>>(h->D, h->d_ctrl, some, 2);
    if ((rc = launchStage(h, MODE_FINAL, ka, kb, kq0, kbt))) return rc;
    h->launches += 2;
-   // maxima on the state at the start of the whole step (tileContainer), stamped t + dt (quirk Q1)
-   // (fused into the final stage launch when that launch's q0 is the step-start state)
-   if (h->nBlocks && kq0 != h->i0) {
-      const double *btm = h->morpho ? h->btv[h->bt0] : nullptr;
-      if (h->oneD)
-         maxima_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
-                                                                       h->d_blockList, h->d_ctrl, u.allActive);
-      else
-         maxima_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->sp(h->i0), h->b0v, btm, h->mp(), h->d_tileMask,
-                                                                       h->d_blockList, h->d_ctrl, u.allActive);
-      h->launches++;
-   }
+   // Maxima (UpdateMaximum*, TimeStepper.f90:519-524, quirk Q1) are those of the state at the start of the whole step,
+   // tileContainer, and ride in the final stage launch of the FIRST hydraulic operator (its q0 is that state).  The
+   // reference runs them again at the end of the second H of a Strang step, on the same tileContainer with a later
+   // stamp: every test there is a strict `>` (or tfirst == -1) against values the first pass has just stored, so that
+   // pass cannot change anything and is not launched (round 1 ran a maxima_kernel here: 2 % of the Strang step).
    CUDA_TRY(h, cudaGetLastError());
    return readCtrl(h);
 }
@@ -887,6 +880,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    D.NX = h->NX; D.NY = h->NY; D.nX = h->nX; D.nY = h->nY; D.nXt = h->nXt; D.nYt = h->nYt;
    D.gtx0 = h->gtx0; D.gty0 = h->gty0; D.gnXt = h->gnXt; D.gnYt = h->gnYt;
    D.mm2HalfTheta = 0.5 * 1.3;
+   D.halfGRhow = 0.5 * p->g * p->rhow;
    D.pitch = h->pitch; D.rows = h->rows;
    D.haloValid = (p->comm_size > 1 && h->globalPeriodic) ? 1 : 0;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;

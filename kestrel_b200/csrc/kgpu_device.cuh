@@ -61,6 +61,7 @@ struct DevParams {
    int bcDirichlet;      // ghost cells of domain-edge tiles carry the boundary values (UpdateTiles.f90:571-664)
    double bcU, bcV, bcPsi;
    double mm2HalfTheta;  // 0.5 * 1.3: MinMod2 half-slope factor of the contracted variant (constant-bank operand)
+   double halfGRhow;     // 0.5 * g * rhow: hydrostatic flux factor of pure-water tiles in the contracted variant
 };
 
 // Device-resident control block: dt selection and rollback flags never leave the GPU
