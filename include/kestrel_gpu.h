@@ -182,7 +182,12 @@ int kgpu_integrate_to(kgpu_handle *h, double tend, int64_t max_steps, kgpu_step_
 /* ---- state out --------------------------------------------------------------- */
 
 /* grid%activeTiles%List in the reference's order (ascending, src/utilities.f90:260).
- * ids may be NULL to query n only. */
+ * ids may be NULL to query n only.
+ * Tile ids everywhere in this interface (upload, download, the two lists, the heights
+ * callback) number the WHOLE tile grid, 1-based with tx fastest, as the reference's
+ * tileContainer index does.  A decomposed handle (comm_size > 1) lists, accepts and
+ * requests only the tiles of its own block (kgpu_comm_block) and answers
+ * KGPU_ERR_ARG for another rank's tile. */
 int kgpu_active_tiles(kgpu_handle *h, int32_t *n, int32_t *ids);
 int kgpu_ghost_tiles(kgpu_handle *h, int32_t *n, int32_t *ids);
 

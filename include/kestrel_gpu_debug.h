@@ -41,6 +41,10 @@ int kgpu_debug_sequential_walk(kgpu_handle *h, int32_t on);
 /* `on` = 1 drives a single periodic device through the walk the decomposed runs use (patches gathered from
  * every rank + canonical slots, kgpu_morpho.cuh) instead of the in-place one. */
 int kgpu_debug_global_walk(kgpu_handle *h, int32_t on);
+/* How a single device runs a morphodynamic Runge-Kutta stage: level 0 = three kernels (E - D, bed, cells: the default, and
+ * what the decomposed runs use), 1 = E - D, then morpho_stage_kernel (bed and cells fused), 2 = morpho_stage_kernel alone.
+ * The fused forms are measured alternatives (slower on B200); a test requires all three to agree bit for bit. */
+int kgpu_debug_morpho_fusion(kgpu_handle *h, int32_t level);
 /* Shrink the device buffer of RedistributeGrid's list to `entries` so that a small test overflows it and
  * exercises the enlargement path (the library's default holds 65 536 entries). */
 int kgpu_debug_redist_capacity(kgpu_handle *h, int32_t entries);

@@ -161,6 +161,7 @@ class Library:
                                                  C.POINTER(C.c_int32)]),
             ("debug_sequential_walk", C.c_int, [C.c_void_p, C.c_int32]),
             ("debug_global_walk", C.c_int, [C.c_void_p, C.c_int32]),
+            ("debug_morpho_fusion", C.c_int, [C.c_void_p, C.c_int32]),
             ("debug_redist_capacity", C.c_int, [C.c_void_p, C.c_int32]),
         ]:
             try:

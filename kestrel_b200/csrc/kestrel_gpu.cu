@@ -119,6 +119,8 @@ struct kgpu_handle {
    uint8_t *d_tileMask = nullptr, *d_tileSource = nullptr;
    int2 *d_blockList = nullptr;
    int nBlocks = 0;
+   int2 *d_blockListM = nullptr;   // tiles of the fused morphodynamic stage kernel (BX2 x MORPHO_STAGE_BY cells)
+   int nBlocksM = 0;
    Ctrl *d_ctrl = nullptr, *h_ctrl = nullptr;
    DevSource *d_sources = nullptr;
    double *d_srcPool = nullptr;
@@ -130,6 +132,9 @@ struct kgpu_handle {
    int64_t nRedistCells = 0, nRedistGrows = 0;   // cells handed to RedistributeGrid / enlargements of its list buffer
    bool debugGlobalWalk = false;                 // kgpu_debug_global_walk (kestrel_gpu_debug.h)
    bool debugSequentialWalk = false;             // kgpu_debug_sequential_walk: one thread walks the list, as the reference does
+   int morphoFusion = 0;   // morphodynamic Runge-Kutta stage on a single device: 0 = E - D, bed, cells as three kernels (fastest
+                           // measured, and what the decomposed runs use), 1 = E - D, then bed + cells fused, 2 = one kernel
+                           // (KGPU_TUNE bits 7 / 8, kgpu_debug_morpho_fusion; DESIGN.md section 5 has the timings)
    int *d_rankMap = nullptr;                     // redistribution wave: list position per cell + the block ticket
 
    // host tile bookkeeping (UpdateTiles.f90)
@@ -186,6 +191,16 @@ __global__ void ctrl_set_dt_kernel(Ctrl *c, double dt) {
 static int roundUp(int a, int b) { return (a + b - 1) / b * b; }
 
 static void tileXY(const kgpu_handle *h, int t0, int &tx, int &ty) { tx = t0 % h->nXt; ty = t0 / h->nXt; }
+// Tile ids across the C-ABI are ids of the WHOLE tile grid (1-based, tx fastest), also in a decomposed run, where
+// the handle stores its own block of nXt x nYt tiles starting at (gtx0, gty0).
+static int globalTileId(const kgpu_handle *h, int t0) { return (h->gty0 + t0 / h->nXt) * h->gnXt + h->gtx0 + t0 % h->nXt + 1; }
+static int localTile0(const kgpu_handle *h, int tile_id) {   // -1: out of range, -2: another rank's tile
+   int g0 = tile_id - 1;
+   if (g0 < 0 || g0 >= h->gnXt * h->gnYt) return -1;
+   int tx = g0 % h->gnXt - h->gtx0, ty = g0 / h->gnXt - h->gty0;
+   if (tx < 0 || tx >= h->nXt || ty < 0 || ty >= h->nYt) return -2;
+   return ty * h->nXt + tx;
+}
 static int tileW(const kgpu_handle *h, int t0) {
    int tx, ty; tileXY(h, t0, tx, ty);
    if (tx == 0) return h->periodic ? (h->nXt - 1) + ty * h->nXt : -1;
@@ -256,6 +271,22 @@ static int refreshMasks(kgpu_handle *h) {
       }
    h->nBlocks = (int)list.size();
    if (h->nBlocks) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockList, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+   std::vector<int2> listM;
+   if (h->morpho && !h->oneD) {   // fused morphodynamic tiles: BX2 x MORPHO_STAGE_BY cells, listed when they overlap an active tile
+      const int BYM = MORPHO_STAGE_BY, nbyM = (h->NY + BYM - 1) / BYM;
+      for (int by = 0; by < nbyM; by++)
+         for (int bx = 0; bx < nbx; bx++) {
+            int tx0 = (bx * BX) / h->nX, tx1 = std::min(bx * BX + BX - 1, h->NX - 1) / h->nX;
+            int ty0 = (by * BYM) / h->nY, ty1 = std::min(by * BYM + BYM - 1, h->NY - 1) / h->nY;
+            bool any = false;
+            for (int ty = ty0; ty <= ty1 && !any; ty++)
+               for (int tx = tx0; tx <= tx1; tx++)
+                  if (h->tstate[ty * h->nXt + tx] == 2) { any = true; break; }
+            if (any) listM.push_back(make_int2(bx, by));
+         }
+      h->nBlocksM = (int)listM.size();
+      if (h->nBlocksM) CUDA_TRY(h, cudaMemcpyAsync(h->d_blockListM, listM.data(), listM.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+   }
    if (h->comm.active) {
       // blocks touching the edge of the local domain are computed first so that their strips can travel
       // while the interior is still being computed
@@ -495,7 +526,7 @@ static int loadHeights(kgpu_handle *h, int t0, const double *given) {
       std::memcpy(hb, given, sizeof(double) * (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1));
    } else if (!onDevice) {
       if (!h->P.heights) { h->err = "no heights callback registered and no b0_vertices given"; return KGPU_ERR_ARG; }
-      if (h->P.heights(h->P.heights_ctx, t0 + 1, hb) != 0) { h->err = "heights callback failed"; return KGPU_ERR_ARG; }
+      if (h->P.heights(h->P.heights_ctx, globalTileId(h, t0), hb) != 0) { h->err = "heights callback failed"; return KGPU_ERR_ARG; }
    }
    int tE = tileE(h, t0), tN = h->oneD ? -1 : tileN(h, t0);
    int tNE = (tE >= 0 && !h->oneD) ? tileN(h, tE) : -1;
@@ -806,7 +837,7 @@ int kgpu_destroy(kgpu_handle *h) {
                         h->topo.yb0, h->topo.yB, h->topo.ytan, h->topo.ygam, h->topo.btc, h->topo.xbt, h->topo.ybt};
       for (int k = 0; k < 15; k++) cudaFree(pl[k]);
    }
-   cudaFree(h->d_blockBoundary); cudaFree(h->d_blockInterior);
+   cudaFree(h->d_blockBoundary); cudaFree(h->d_blockInterior); cudaFree(h->d_blockListM);
    for (int k = 0; k < 4; k++) { cudaFree(h->comm.sendBuf[k]); cudaFree(h->comm.recvBuf[k]); }
    if (h->comm.nccl && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->comm.nccl);
    if (h->comm.evBoundary) cudaEventDestroy(h->comm.evBoundary);
@@ -928,6 +959,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    int nbx = (h->NX + BX - 1) / BX, nby = (h->NY + BY - 1) / BY;
    if (cudaMalloc(&h->d_tileMask, msz) != cudaSuccess || cudaMalloc(&h->d_tileSource, msz) != cudaSuccess) return fail("masks");
    if (cudaMalloc(&h->d_blockList, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess) return fail("blocklist");
+   if (h->morpho && cudaMalloc(&h->d_blockListM, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess) return fail("blocklist");
    if (p->comm_size > 1 && (cudaMalloc(&h->d_blockBoundary, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess ||
                             cudaMalloc(&h->d_blockInterior, sizeof(int2) * (size_t)nbx * nby) != cudaSuccess)) return fail("blocklists");
    if (cudaMalloc(&h->d_ctrl, sizeof(Ctrl)) != cudaSuccess || cudaMallocHost(&h->h_ctrl, sizeof(Ctrl)) != cudaSuccess) return fail("ctrl");
@@ -969,6 +1001,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       h->tune = 31;  // measured on B200 at 4096^2 (round 1): bit 1 +3.9 %, bit 2 +1.8 %, bit 3 +0.5 %, bit 0 +-0, bit 4 +2.2 %; all five +7.9 %
       if (const char *e = std::getenv("KGPU_TUNE")) h->tune = std::atoi(e);                          // tuning knob (StageArgs::tune)
       h->useSpec = !(h->tune & 64);
+      h->morphoFusion = (h->tune & 256) ? 2 : (h->tune & 128) ? 1 : 0;
    }
    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail("init sync");
    *out = h;
@@ -979,8 +1012,8 @@ int kgpu_upload_tile(kgpu_handle *h, int32_t tile_id, const double *u13, const d
                      const double *maxima, const double *tfirst, int32_t contains_source) {
    if (!h || !u13) return KGPU_ERR_ARG;
    cudaSetDevice(h->dev);
-   int t0 = tile_id - 1;
-   if (t0 < 0 || t0 >= h->nTiles) { h->err = "tile id out of range"; return KGPU_ERR_ARG; }
+   int t0 = localTile0(h, tile_id);
+   if (t0 < 0) { h->err = t0 == -1 ? "tile id out of range" : "tile belongs to another rank's block (kgpu_comm_block)"; return KGPU_ERR_ARG; }
    int rc;
    if (b0_vertices && (rc = loadHeights(h, t0, b0_vertices))) return rc;
    if ((rc = addTile(h, t0, false))) return rc;
@@ -1147,24 +1180,21 @@ int kgpu_integrate_to(kgpu_handle *h, double tend, int64_t max_steps, kgpu_step_
 int kgpu_active_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
    if (!h || !n) return KGPU_ERR_ARG;
    *n = (int32_t)h->activeList.size();
-   if (ids) for (size_t k = 0; k < h->activeList.size(); k++) {
-      int t0 = h->activeList[k] - 1;
-      ids[k] = (h->gty0 + t0 / h->nXt) * h->gnXt + h->gtx0 + t0 % h->nXt + 1;
-   }
+   if (ids) for (size_t k = 0; k < h->activeList.size(); k++) ids[k] = globalTileId(h, h->activeList[k] - 1);
    return KGPU_OK;
 }
 int kgpu_ghost_tiles(kgpu_handle *h, int32_t *n, int32_t *ids) {
    if (!h || !n) return KGPU_ERR_ARG;
    *n = (int32_t)h->ghostList.size();
-   if (ids) for (size_t k = 0; k < h->ghostList.size(); k++) ids[k] = h->ghostList[k];
+   if (ids) for (size_t k = 0; k < h->ghostList.size(); k++) ids[k] = globalTileId(h, h->ghostList[k] - 1);
    return KGPU_OK;
 }
 
 int kgpu_download_tile(kgpu_handle *h, int32_t tile_id, double *u13, double *b0_vertices, double *bt_vertices, double *maxima, double *tfirst) {
    if (!h) return KGPU_ERR_ARG;
    cudaSetDevice(h->dev);
-   int t0 = tile_id - 1;
-   if (t0 < 0 || t0 >= h->nTiles) { h->err = "tile id out of range"; return KGPU_ERR_ARG; }
+   int t0 = localTile0(h, tile_id);
+   if (t0 < 0) { h->err = t0 == -1 ? "tile id out of range" : "tile belongs to another rank's block (kgpu_comm_block)"; return KGPU_ERR_ARG; }
    int nX = h->nX, nY = h->nY;
    size_t ncell = (size_t)nX * nY, nv = (size_t)(nX + 1) * (nY + 1), nvu = (size_t)(nX + 1) * (h->oneD ? 1 : nY + 1);
    int tx, ty; tileXY(h, t0, tx, ty);
@@ -1347,6 +1377,11 @@ int kgpu_debug_rhs(kgpu_handle *h, int32_t substep, double *E4, double *I, doubl
 int kgpu_debug_sequential_walk(kgpu_handle *h, int32_t on) {
    if (!h) return KGPU_ERR_ARG;
    h->debugSequentialWalk = on != 0;
+   return KGPU_OK;
+}
+int kgpu_debug_morpho_fusion(kgpu_handle *h, int32_t level) {
+   if (!h || level < 0 || level > 2) return KGPU_ERR_ARG;
+   h->morphoFusion = level;
    return KGPU_OK;
 }
 int kgpu_debug_global_walk(kgpu_handle *h, int32_t on) {

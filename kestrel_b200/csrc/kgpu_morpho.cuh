@@ -605,4 +605,159 @@ __global__ void redist_scatter_kernel(const DevParams P, const RedistScatterArgs
       }
 }
 
+// ------------------------------------------------------------------ one Runge-Kutta stage of M in ONE launch
+// morpho_emd_kernel + morpho_bed_kernel + morpho_cell_kernel fused (single device): E - D is evaluated over the tile
+// plus one cell (the four cells around every vertex of the tile) into shared memory, the stage bed at the tile's
+// (BX+1) x (BY+1) vertices from it, and the linear update of w and Hn psi of the tile's cells from that bed -- the
+// E - D plane and the second read of the new bed never touch HBM, and two of the three halo fills between the
+// kernels disappear.  Every statement is the one of the kernel it comes from (same functions, same operand order),
+// so the results are those of the three-kernel path bit for bit; decomposed runs keep that path (they exchange E - D
+// and the bed between the kernels), and tests/test_gpu_multi.py requires both to agree.
+// What must be valid around the tile: w, Hn psi, b0c, cBt, cBx, cBy, U, V one cell out and cHn two cells out (the
+// periodic images are filled by the host after every stage; out-of-domain and inactive cells contribute E - D = 0 as
+// the never-written E - D plane did), the vertex arrays b0v, bt0, btk two vertices out.
+// Tile: 32 x 13 cells for the 2-D kernel -- (32+2) x (13+2) = 510 E - D evaluations fill two passes of 256 threads
+// (32 x 14 would need a third pass for 32 leftover cells of the most expensive phase: measured +30 % on the kernel).
+constexpr int MORPHO_STAGE_BY = 13;
+// EMDPLANE = true: E - D comes from the plane morpho_emd_kernel has just written (one evaluation per cell: the closures
+// -- pow, tanh, log -- are compute-bound and the 23 % of extra evaluations in the ring around the tile cost more than
+// the plane's 16 B per cell: measured); false: evaluated here over tile + 1 cell.
+template <int BX, int BY, bool ONED, bool EMDPLANE>
+__global__ void __launch_bounds__(256, 4) morpho_stage_kernel(const DevParams P, const MorphoArgs A, const int2 *blocks) {
+   constexpr int EX = BX + 2, EY = ONED ? 1 : BY + 2;   // E - D: tile + 1 cell
+   constexpr int VX = BX + 1, VY = ONED ? 1 : BY + 1;   // vertices of the tile
+   __shared__ double s_emd[EX * EY];
+   __shared__ double s_bt[VX * VY];
+   const int2 bo = blocks[blockIdx.x];
+   const int x0 = bo.x * BX, y0 = ONED ? 0 : bo.y * BY;
+   const int tid = threadIdx.x;
+   const bool wrapOrHalo = P.periodic || P.haloValid;
+   const double eps = P.Hneps;
+   // ---- E - D (morpho_emd_kernel; MorphodynamicRHS.f90:96-145)
+   for (int k = tid; k < EX * EY; k += blockDim.x) {
+      const int ci = x0 - 1 + k % EX, cj = ONED ? 0 : y0 - 1 + k / EX;
+      double val = 0.0;
+      const bool inDomain = ci >= 0 && ci < P.NX && cj >= 0 && cj < P.NY;
+      const bool image = wrapOrHalo && ci >= -1 && ci <= P.NX && cj >= (ONED ? 0 : -1) && cj <= (ONED ? 0 : P.NY);
+      if (EMDPLANE) {   // morpho_bed_kernel's read of the plane: wrapped index on a periodic device, zero outside the domain
+         if (inDomain || image) {
+            int i = ci, j = cj;
+            if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
+            val = A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
+         }
+      } else if ((inDomain || image) && cellTileActive(P, A.tileMask, A.allActive, ci, cj)) {
+         const size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+         CellState q;
+         q.w = A.w[g]; q.hpsi = A.hpsi[g]; q.hu = 0.0; q.hv = 0.0;
+         q.b0 = A.b0c[g]; q.bt = A.cBt[g]; q.bx = A.cBx[g]; q.by = A.cBy[g];
+         desingularise(P, q, false);
+         q.u = A.U[g]; q.v = A.V[g];
+         auto nbHn = [&](int i, int j) -> double {
+            if (cellTileActive(P, A.tileMask, A.allActive, i, j)) return A.cHn[(size_t)(j + YO) * P.pitch + (i + XO)];
+            return storedHn(P, A.w, A.b0v, A.btk, i, j);
+         };
+         bool dry = q.Hn < eps || nbHn(ci - 1, cj) < eps || nbHn(ci + 1, cj) < eps;
+         if (!P.oneD) dry = dry || nbHn(ci, cj - 1) < eps || nbHn(ci, cj + 1) < eps;
+         val = dry ? 0.0 : erosionMinusDeposition(P, q);
+      }
+      s_emd[k] = val;
+   }
+   __syncthreads();
+   // ---- the stage bed at the tile's vertices (morpho_bed_kernel; MorphodynamicRHS.f90:154-305, TimeStepper.f90:574-581)
+   const int nvy = P.oneD ? 1 : P.NY + 1;
+   for (int k = tid; k < VX * VY; k += blockDim.x) {
+      const int lvx = k % VX, lvy = k / VX;
+      const int vi = x0 + lvx, vj = ONED ? 0 : y0 + lvy;
+      double val = 0.0;
+      if (vi <= P.NX && vj < nvy) {
+         const size_t gv = (size_t)(vj + YO) * P.pitch + (vi + XO);
+         bool any = false;
+         for (int dj = (P.oneD ? 0 : -1); dj <= 0; dj++)
+            for (int di = -1; di <= 0; di++) {
+               int i = vi + di, j = vj + dj;
+               if (!wrapOrHalo && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) continue;
+               if (cellTileActive(P, A.tileMask, A.allActive, i, j)) any = true;
+            }
+         if (!any) val = A.btn[gv];   // not a vertex of an active tile: the array keeps what it holds
+         else {
+            const double psib = 1.0 - P.BedPorosity;
+            double rhs;
+            // E - D of the cell (vi + di, vj + dj), di, dj in {-1, 0}: tile-local (lvx + di + 1, lvy + dj + 1)
+            auto emd = [&](int di, int dj) -> double { return s_emd[(ONED ? 0 : lvy + dj + 1) * EX + lvx + di + 1]; };
+            auto slopes = [&](int i, int j, double &bx_, double &by_) {
+               if (cellTileActive(P, A.tileMask, A.allActive, i, j)) {
+                  size_t gc = (size_t)(j + YO) * P.pitch + (i + XO);
+                  bx_ = A.cBx[gc]; by_ = A.cBy[gc];
+               } else {
+                  double b0c_, btc_;
+                  centreTopoGlobal(P, A.b0v, A.btk, i, j, b0c_, btc_, bx_, by_);
+               }
+            };
+            if (!P.oneD) {
+               double bx[4], by[4];
+               slopes(vi - 1, vj - 1, bx[0], by[0]);
+               slopes(vi - 1, vj, bx[1], by[1]);
+               slopes(vi, vj - 1, bx[2], by[2]);
+               slopes(vi, vj, bx[3], by[3]);
+               double dbdx = 0.25 * kahan4(bx[0], bx[1], bx[2], bx[3]);
+               double dbdy = 0.25 * kahan4(by[0], by[1], by[2], by[3]);
+               double gam = gamma2(P, dbdx, dbdy);
+               rhs = -0.25 * gam / psib * kahan4(emd(-1, -1), emd(-1, 0), emd(0, -1), emd(0, 0));
+            } else {
+               bool lAct = (wrapOrHalo || vi - 1 >= 0) && cellTileActive(P, A.tileMask, A.allActive, vi - 1, 0);
+               bool rAct = (wrapOrHalo || vi < P.NX) && cellTileActive(P, A.tileMask, A.allActive, vi, 0);
+               double bxl = 0.0, bxr = 0.0, byd;
+               if (lAct) slopes(vi - 1, 0, bxl, byd);
+               if (rAct) slopes(vi, 0, bxr, byd);
+               if (lAct && rAct) {
+                  double dbdx = 0.5 * (bxl + bxr);
+                  double gam = gamma2(P, dbdx, 0.0);
+                  rhs = -0.5 * gam * (emd(-1, 0) + emd(0, 0)) / psib;
+               } else {
+                  double dbdx = 0.5 * (lAct ? bxl : bxr);
+                  double gam = gamma2(P, dbdx, 0.0);
+                  rhs = -0.5 * gam * (lAct ? emd(-1, 0) : emd(0, 0)) / psib;
+               }
+            }
+            if (A.a0 == 0.0) val = A.bt0[gv] + A.dtMorpho * rhs;
+            else val = A.a0 * A.bt0[gv] + A.a1 * (A.btk[gv] + A.dtMorpho * rhs);
+            val = fmax(-P.EroDepth, val);
+            // (neighbouring tiles write the vertices they share with this one, with the same bits; the periodic aliases
+            // NX, NY are left to the halo fill, as in morpho_bed_kernel)
+            if (!(P.periodic && (vi == P.NX || (!P.oneD && vj == P.NY)))) A.btn[gv] = val;
+         }
+      }
+      s_bt[k] = val;
+   }
+   __syncthreads();
+   // ---- w, Hn psi and the centre planes of the new bed (morpho_cell_kernel; TimeStepper.f90:587-610)
+   for (int k = tid; k < BX * BY; k += blockDim.x) {
+      const int tx = k % BX, ty = ONED ? 0 : k / BX;
+      const int ci = x0 + tx, cj = ONED ? 0 : y0 + ty;
+      if (ci >= P.NX || cj >= P.NY) continue;
+      if (!cellTileActive(P, A.tileMask, A.allActive, ci, cj)) continue;
+      const size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
+      const double va = A.b0v[g], vb = A.b0v[g + 1], vc = ONED ? 0.0 : A.b0v[g + P.pitch], vd = ONED ? 0.0 : A.b0v[g + P.pitch + 1];
+      const double ta = s_bt[ty * VX + tx], tb = s_bt[ty * VX + tx + 1];
+      const double tc = ONED ? 0.0 : s_bt[(ty + 1) * VX + tx], td = ONED ? 0.0 : s_bt[(ty + 1) * VX + tx + 1];
+      double b0c, btnc, bxn, byn;
+      centreTopoVals(P, va, vb, vc, vd, ta, tb, tc, td, b0c, btnc, bxn, byn);
+      const double bt0c = A.zBt[g];
+      double gamold = A.zGam[g], gamnew = gamma2(P, bxn, byn);
+      double Hn_old = computeHn(A.w0[g], b0c, bt0c, gamold);
+      double db = btnc - bt0c;
+      double w = -db / gamnew / gamnew;
+      w = w + btnc;
+      w = w + Hn_old * gamold / gamnew / gamnew;
+      w = w + b0c;
+      A.wn[g] = w;
+      double Hnpsi = -(1.0 - P.BedPorosity) * db / gamnew;
+      Hnpsi = Hnpsi + A.hpsi0[g] * gamold / gamnew;
+      A.hpsin[g] = Hnpsi;
+      A.nBt[g] = btnc; A.nBx[g] = bxn; A.nBy[g] = byn;
+      double Hn_new = computeHn(w, b0c, btnc, gamnew);
+      A.nHn[g] = Hn_new < 0.0 ? 0.0 : Hn_new;
+   }
+}
+
 }  // namespace kgpu

@@ -117,6 +117,28 @@ static int redistributeAcrossRanks(kgpu_handle *h, int nLocal, int M, int R1, in
 template <bool ONED>
 static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    constexpr int BX = ONED ? BX1 : BX2, BY = ONED ? BY1 : BY2;
+   if (!h->comm.active && h->morphoFusion > 0) {
+      // measured alternatives (slower than the three kernels below on B200): the stage bed and the cell
+      // update fused (morpho_stage_kernel), E - D from its plane (level 1) or evaluated in the same launch (level 2); then the
+      // periodic images of the new bed and of the six centre planes the next stage reads
+      if (h->morphoFusion == 2) {
+         if (ONED) morpho_stage_kernel<BX1, BY1, true, false><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a, h->d_blockList);
+         else morpho_stage_kernel<BX2, MORPHO_STAGE_BY, false, false><<<h->nBlocksM, NTHREADS, 0, h->stream>>>(h->D, a, h->d_blockListM);
+         h->launches++;
+      } else {   // E - D once per cell into its plane, then the bed and the cell update fused
+         morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
+         if (ONED) morpho_stage_kernel<BX1, BY1, true, true><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a, h->d_blockList);
+         else morpho_stage_kernel<BX2, MORPHO_STAGE_BY, false, true><<<h->nBlocksM, NTHREADS, 0, h->stream>>>(h->D, a, h->d_blockListM);
+         h->launches += 2;
+      }
+      double *pl[1] = {a.btn};
+      int rc = fillHaloPlanes(h, pl, 1, true);
+      if (rc) return rc;
+      double *pc[6] = {a.wn, a.hpsin, a.nBt, a.nBx, a.nBy, a.nHn};
+      rc = fillHaloPlanes(h, pc, 6, false);
+      CUDA_TRY(h, cudaGetLastError());
+      return rc;
+   }
    morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
    if (h->comm.active) {   // the bed kernel reads E - D of the cells across the block edge (single device: by wrapped index)
       double *pe[1] = {a.EmD};
@@ -155,7 +177,8 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
       morpho_prepare_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
                                                                             h->topo.b0c, h->topo.btc, h->topo.bxc, h->topo.byc, h->Um, h->Vm,
                                                                             h->mcHn0, h->d_tileMask, h->d_blockList, allAct);
-   { double *ph[1] = {h->mcHn0}; if ((rc = fillHaloPlanes(h, ph, 1, false))) return rc; }
+   // (the fused stage kernel evaluates E - D in the cells around the tile: the frozen velocities need their images too)
+   { double *ph[3] = {h->mcHn0, h->Um, h->Vm}; if ((rc = fillHaloPlanes(h, ph, 3, false))) return rc; }
    h->launches++;
    double dt_morpho = 2.0 * dt_hydro;
    MorphoArgs a;

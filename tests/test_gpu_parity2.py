@@ -286,3 +286,77 @@ def test_many_sources_long_series(oracle_lib, gpu_lib):
     for d, name in enumerate(NAMES):
         assert np.array_equal(qo[d], qg[d]), (name, rel_linf(qg[d], qo[d]))
     so.close(); sg.close()
+
+
+# ------------------------------------------------------------------ the fused morphodynamic stage
+@pytest.mark.parametrize("case,kw", [
+    ("case_cap_morpho_2d.txt", dict(tend=1.0, Nout=1)),
+    ("case_flux_morpho_2d.txt", dict(tend=5.0, Nout=1)),
+    ("case_cap_morpho.txt", dict(tend=4.0, Nout=1)),
+    ("case_lake_at_rest_morpho_2d.txt", dict(tend=1.0, Nout=1)),
+    ("case_tile_indep_dynamic_20m.txt", dict(tend=2.0, Nout=1)),
+])
+@pytest.mark.parametrize("arithmetic", [0, 1])
+def test_fused_morpho_stage_equals_the_three_kernels(gpu_lib, case, kw, arithmetic):
+    """morpho_stage_kernel (stage bed and cell update in one launch per Runge-Kutta stage, level 1; with E - D as well,
+    level 2) against the three kernels it fuses, which are the default: same statements, same bits -- state, bed,
+    maxima, step and rollback counts -- on reference inputs with dynamic tiles, 1-D and 2-D, periodic and not."""
+    from kestrel_b200.host.inputfile import read_input_file
+    from kestrel_b200.host.run import Simulation
+
+    def run(level):
+        rs = read_input_file(os.path.join(INPUTS, case))
+        for k, v in kw.items():
+            setattr(rs, k, v)
+        rs.arithmetic = arithmetic
+        rs.finalize()
+        sim = Simulation(rs, gpu_lib)
+        assert gpu_lib.debug_morpho_fusion(sim.stepper.h, level) == 0
+        return sim.run()
+    b = run(0)
+    for level in (1, 2):
+        a = run(level)
+        assert [(i.t, i.nsteps, i.nrefines, i.ntiles_added) for i in a.infos] == [(i.t, i.nsteps, i.nrefines, i.ntiles_added) for i in b.infos]
+        assert a.infos[-1].nsteps > 3
+        sa, sb = a.snapshots[-1], b.snapshots[-1]
+        for name, (err, exact) in compare_snapshots(sa, sb).items():
+            assert exact, (level, name, err)
+        for k in sa:
+            assert np.array_equal(sa[k]["bt"], sb[k]["bt"]) and np.array_equal(sa[k]["maxima"], sb[k]["maxima"])
+
+
+def test_morpho_fusion_levels_by_env(gpu_lib, monkeypatch):
+    """KGPU_TUNE bits 7 / 8 select the same alternatives at handle creation (how bench.py times them): fewer launches,
+    same bits."""
+    rs = dambreak_runset(2, 32, morpho=True)
+    q4, b0v = dambreak_state(rs)
+    sa = domain_stepper(gpu_lib, rs, q4, b0v)
+    ia = sa.integrate_to(1e9, 15)
+    qa, ba = sa.download_domain(True)
+    last = sa.lib.launch_count(sa.h)
+    for bit in (128, 256):
+        monkeypatch.setenv("KGPU_TUNE", str(31 + bit))
+        sb = domain_stepper(gpu_lib, rs, q4, b0v)
+        monkeypatch.delenv("KGPU_TUNE")
+        ib = sb.integrate_to(1e9, 15)
+        assert (ia.t, ia.nsteps, ia.nrefines) == (ib.t, ib.nsteps, ib.nrefines)
+        qb, bb = sb.download_domain(True)
+        assert np.array_equal(qa, qb) and np.array_equal(ba, bb)
+        assert sb.lib.launch_count(sb.h) < last
+        last = sb.lib.launch_count(sb.h)
+        sb.close()
+    sa.close()
+
+
+def test_fused_morpho_stage_periodic_redistribution(gpu_lib):
+    """The same on the periodic thin-layer dam-break whose every step redistributes excess deposit."""
+    rs = thin_dambreak_runset(2, 32)
+    q4, b0v = dambreak_state(rs)
+    sa, sb = domain_stepper(gpu_lib, rs, q4, b0v), domain_stepper(gpu_lib, rs, q4, b0v)
+    assert gpu_lib.debug_morpho_fusion(sb.h, 1) == 0
+    ia, ib = sa.integrate_to(1e9, 25), sb.integrate_to(1e9, 25)
+    assert (ia.t, ia.nsteps, ia.nrefines) == (ib.t, ib.nsteps, ib.nrefines)
+    (qa, ba), (qb, bb) = sa.download_domain(True), sb.download_domain(True)
+    assert np.array_equal(qa, qb) and np.array_equal(ba, bb)
+    assert sa.morpho_stats()[0] == sb.morpho_stats()[0] > 1000
+    sa.close(); sb.close()

@@ -1,0 +1,12 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+( timeout 900 python -m pytest tests/test_gpu_parity2.py -m gpu -q -x -k "fused or maxima_moving or morpho_parity or redistribution" 2>&1 | tail -6 ) > gpurun_out/r02_tests9.log 2>&1
+cat gpurun_out/r02_tests9.log
+timeout 900 python bench.py --workload morpho --size 8192 --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/r02_bench_morpho_8192_v7.json 2> gpurun_out/r02_bench_morpho_8192_v7.err
+tail -1 gpurun_out/r02_bench_morpho_8192_v7.json | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('morpho v6', d['value'], d['ms_per_step'], d['roofline']['step_frac_of_hbm_roofline'], d['config'].get('rolled_back_attempts'), d.get('other_arithmetic'))"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_morpho_4096_v7.csv \
+   python bench.py --workload morpho --size 4096 --steps 2 --warmup 3 --no-cpu --no-e2e --no-faithful > gpurun_out/r02_ncu_list_morpho_v7.log 2>&1
