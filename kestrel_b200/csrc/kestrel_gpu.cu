@@ -143,6 +143,12 @@ struct kgpu_handle {
    std::vector<int> activeList, ghostList;  // 1-based ids
    std::vector<int> seedFlags;
    bool firstScan = true, masksDirty = true;
+   // decomposed run on a non-periodic domain: dynamic tiles through the replicated table (kgpu_dyn_host.inl)
+   bool dyn = false;
+   kgpu::TileTable gt;
+   size_t opsDone = 0;               // entries of gt.ops already executed on this device
+   std::vector<int> gSeed, gSource;  // per tile of the whole grid: seed flags of the first scan, containsSource
+   int *d_gflags = nullptr, *h_gflags = nullptr;
 
    double t = 0.0, dtgrid = 1.0e-5;
    int64_t nsteps = 0, nrefines = 0, ntilesAdded = 0, launches = 0;
@@ -162,7 +168,8 @@ struct kgpu_handle {
    RasterDesc raster = {nullptr, 0, 0, 0, 0, 0, 0, 0, 0};  // DEM section resampled on the device (elev == nullptr: not set)
    double *d_raster = nullptr;
 
-   bool allActive() const { return (int)activeList.size() == nTiles; }
+   // (a block of a dynamic decomposed run is never treated as all-active: the tiles around it need not be)
+   bool allActive() const { return !dyn && (int)activeList.size() == nTiles; }
    StatePtrs sp(int k) const { StatePtrs s; for (int d = 0; d < 4; d++) s.q[d] = S[k][d]; return s; }
    MaximaPtrs mp() const {
       MaximaPtrs m;
@@ -244,8 +251,13 @@ static int refreshMasks(kgpu_handle *h) {
          int sx = tx, sy = ty;
          if (h->periodic) { sx = (tx + h->nXt) % h->nXt; sy = (ty + h->nYt) % h->nYt; }
          if (sx < 0 || sx >= h->nXt || sy < 0 || sy >= h->nYt) {
-            // ring tile owned by a neighbouring rank: decomposed runs keep every tile active
+            // ring tile owned by a neighbouring rank: periodic decomposed runs keep every tile active, dynamic ones
+            // read the replicated table (outside the domain: nothing)
             if (h->comm.active && h->globalPeriodic) mask[(size_t)(ty + 1) * mw + tx + 1] = 2;
+            else if (h->dyn) {
+               int gx = h->gtx0 + tx, gy = h->gty0 + ty;
+               if (gx >= 0 && gx < h->gnXt && gy >= 0 && gy < h->gnYt) mask[(size_t)(ty + 1) * mw + tx + 1] = (uint8_t)h->gt.tstate[gy * h->gnXt + gx];
+            }
             continue;
          }
          int t0 = sy * h->nXt + sx;
@@ -439,7 +451,7 @@ static int computeTopo(kgpu_handle *h, int kbt) {
 // One fused RHS(+stage update) launch.  mode: StageMode; qin / qout = state buffer indices
 // (MODE_RHS writes E0/I0 instead of a state).
 static int launchStage(kgpu_handle *h, int mode, int kin, int kout, int kq0, int kbt) {
-   if (h->nBlocks == 0) return 0;
+   if (h->nBlocks == 0 && !h->comm.active) return 0;   // (a rank without active blocks still takes part in the exchange)
    StageArgs a;
    for (int d = 0; d < 4; d++) {
       a.qin[d] = h->S[kin][d];
@@ -494,8 +506,7 @@ static int readCtrl(kgpu_handle *h) {
 }
 
 // =========================================================================== topography + tiles
-static int defaultTile(kgpu_handle *h, int t0, int kind) {
-   int tx, ty; tileXY(h, t0, tx, ty);
+static int defaultTileXY(kgpu_handle *h, int tx, int ty, int kind) {
    dim3 grid((h->nX + 127) / 128, h->nY);
    const kgpu_params &P = h->P;
    AllStates all;
@@ -507,6 +518,10 @@ static int defaultTile(kgpu_handle *h, int t0, int kind) {
    h->launches++;
    CUDA_TRY(h, cudaGetLastError());
    return 0;
+}
+static int defaultTile(kgpu_handle *h, int t0, int kind) {
+   int tx, ty; tileXY(h, t0, tx, ty);
+   return defaultTileXY(h, tx, ty, kind);
 }
 static int ghostData(kgpu_handle *h, int t0) {
    bool dirichlet = (h->P.bcs == KGPU_BC_DIRICHLET) && onDomainEdge(h, t0);
@@ -612,7 +627,9 @@ static int addTile(kgpu_handle *h, int t0, bool countIt) {
 }
 
 // CheckIfNearBoundaries (TimeStepper.f90:924-1150): flags on the device, list replay on the host
+static int dynCheckIfNearBoundaries(kgpu_handle *h);
 static int checkIfNearBoundaries(kgpu_handle *h) {
+   if (h->dyn) return dynCheckIfNearBoundaries(h);
    if (h->allActive()) { h->firstScan = false; return 0; }
    int nAct = (int)h->activeList.size();
    if (nAct == 0) return 0;
@@ -737,6 +754,7 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
 }
 
 #include "kgpu_comm_host.inl"
+#include "kgpu_dyn_host.inl"
 #include "kgpu_morpho_host.inl"
 
 static int integrateTo(kgpu_handle *h, double tend, int64_t maxSteps, kgpu_step_info *info) {
@@ -830,8 +848,8 @@ int kgpu_destroy(kgpu_handle *h) {
    for (int k = 0; k < 11; k++) cudaFree(h->mx[k]);
    cudaFree(h->d_tileMask); cudaFree(h->d_tileSource); cudaFree(h->d_blockList); cudaFree(h->d_ctrl);
    cudaFree(h->d_rankMap); cudaFree(h->d_raster);
-   cudaFree(h->d_sources); cudaFree(h->d_srcPool); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_redist); cudaFree(h->d_maps);
-   cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_redist);
+   cudaFree(h->d_sources); cudaFree(h->d_srcPool); cudaFree(h->d_stage); cudaFree(h->d_tileList); cudaFree(h->d_flags); cudaFree(h->d_gflags); cudaFree(h->d_redist); cudaFree(h->d_maps);
+   cudaFreeHost(h->h_ctrl); cudaFreeHost(h->h_stage); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_gflags); cudaFreeHost(h->h_redist);
    {
       double *pl[15] = {h->topo.b0c, h->topo.bxc, h->topo.byc, h->topo.gamc, h->topo.xb0, h->topo.xB, h->topo.xtan, h->topo.xgam,
                         h->topo.yb0, h->topo.yB, h->topo.ytan, h->topo.ygam, h->topo.btc, h->topo.xbt, h->topo.ybt};
@@ -887,15 +905,23 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       c.size = p->comm_size; c.rank = p->comm_rank; c.px = p->comm_px; c.py = p->comm_py;
       bool okc = c.px >= 1 && c.py >= 1 && c.px * c.py == c.size && c.rank >= 0 && c.rank < c.size &&
                  p->nXtiles % c.px == 0 && p->nYtiles % c.py == 0 && !(h->oneD && c.py != 1);
-      if (!okc || !h->globalPeriodic) {
-         fprintf(stderr, "kgpu_create: decomposition needs px*py = size, tiles divisible by px, py and periodic bcs\n");
+      // periodic domains run all-active (kgpu_upload_domain); the others keep dynamic tiles through the replicated
+      // tile table (kgpu_dyn_host.inl) -- hydraulic operator only so far
+      const bool okd = h->globalPeriodic || (!h->morpho && p->nXpertile >= 3 && (h->oneD || p->nYpertile >= 3));
+      if (!okc || !okd) {
+         fprintf(stderr, "kgpu_create: decomposition needs px*py = size and tiles divisible by px, py; without periodic bcs also "
+                         "MorphodynamicsOn = 0 and tiles of at least 3 cells\n");
          delete h;
          return okc ? KGPU_ERR_UNSUPPORTED : KGPU_ERR_ARG;
       }
+      h->dyn = !h->globalPeriodic;
       c.rx = c.rank % c.px; c.ry = c.rank / c.px;
       h->nXt = p->nXtiles / c.px; h->nYt = p->nYtiles / c.py;
       h->gtx0 = c.rx * h->nXt; h->gty0 = c.ry * h->nYt;
-      auto rk = [&](int x, int y) { return ((y + c.py) % c.py) * c.px + ((x + c.px) % c.px); };
+      auto rk = [&](int x, int y) {   // -1: the domain ends there
+         if (h->dyn && (x < 0 || x >= c.px || y < 0 || y >= c.py)) return -1;
+         return ((y + c.py) % c.py) * c.px + ((x + c.px) % c.px);
+      };
       if (c.px > 1) { c.west = rk(c.rx - 1, c.ry); c.east = rk(c.rx + 1, c.ry); }
       if (c.py > 1) { c.south = rk(c.rx, c.ry - 1); c.north = rk(c.rx, c.ry + 1); }
       h->periodic = false;  // the local block does not wrap onto itself (per direction handled in exchangeHalo)
@@ -913,7 +939,7 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    D.mm2HalfTheta = 0.5 * 1.3;
    D.halfGRhow = 0.5 * p->g * p->rhow;
    D.pitch = h->pitch; D.rows = h->rows;
-   D.haloValid = (p->comm_size > 1 && h->globalPeriodic) ? 1 : 0;
+   D.haloValid = p->comm_size > 1 ? 1 : 0;
    D.oneD = h->oneD; D.periodic = h->periodic; D.geom = p->geometric_factors != 0; D.morpho = h->morpho;
    D.bcDirichlet = p->bcs == KGPU_BC_DIRICHLET ? 1 : 0; D.bcU = p->bcsuval; D.bcV = p->bcsvval; D.bcPsi = p->bcspsival;
    D.limiter = p->limiter; D.drag = p->drag; D.erosion = p->erosion; D.deposition = p->deposition;
@@ -932,6 +958,10 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
 
    h->tstate.assign(h->nTiles, 0); h->hasSource.assign(h->nTiles, 0); h->loaded.assign(h->nTiles, 0); h->seedFlags.assign(h->nTiles, 0);
    h->t = p->tstart;
+   if (h->dyn) {
+      h->gt.init(h->gnXt, h->gnYt, false, h->oneD, p->bcs == KGPU_BC_HALT);
+      h->gSeed.assign(h->gt.nTiles(), 0); h->gSource.assign(h->gt.nTiles(), 0);
+   }
 
    auto fail = [&](const char *what) { fprintf(stderr, "kgpu_create: %s: %s\n", what, cudaGetErrorString(cudaGetLastError())); kgpu_destroy(h); return KGPU_ERR_CUDA; };
    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
@@ -974,6 +1004,11 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
    if (cudaMalloc(&h->d_stage, h->stageElems * sizeof(double)) != cudaSuccess || cudaMallocHost(&h->h_stage, h->stageElems * sizeof(double)) != cudaSuccess) return fail("stage");
    if (cudaMalloc(&h->d_tileList, sizeof(int) * h->nTiles) != cudaSuccess || cudaMalloc(&h->d_flags, sizeof(int) * h->nTiles) != cudaSuccess ||
        cudaMallocHost(&h->h_flags, sizeof(int) * h->nTiles) != cudaSuccess) return fail("flags");
+   if (h->dyn) {
+      size_t nb = sizeof(int) * (size_t)h->gt.nTiles();
+      if (cudaMalloc(&h->d_gflags, nb) != cudaSuccess || cudaMallocHost(&h->h_gflags, nb) != cudaSuccess) return fail("global flags");
+      std::memset(h->h_gflags, 0, nb);
+   }
    if (h->morpho) {
       h->redistCap = 1 << 16;
       if (cudaMalloc(&h->d_redist, sizeof(RedistEntry) * h->redistCap) != cudaSuccess ||
@@ -1012,6 +1047,10 @@ int kgpu_upload_tile(kgpu_handle *h, int32_t tile_id, const double *u13, const d
                      const double *maxima, const double *tfirst, int32_t contains_source) {
    if (!h || !u13) return KGPU_ERR_ARG;
    cudaSetDevice(h->dev);
+   if (h->dyn) {
+      if (!h->comm.active) { h->err = "call kgpu_comm_attach before uploading"; return KGPU_ERR_ARG; }
+      return dynUploadTile(h, tile_id, u13, b0_vertices, bt_vertices, maxima, tfirst, contains_source);
+   }
    int t0 = localTile0(h, tile_id);
    if (t0 < 0) { h->err = t0 == -1 ? "tile id out of range" : "tile belongs to another rank's block (kgpu_comm_block)"; return KGPU_ERR_ARG; }
    int rc;

@@ -10,7 +10,7 @@
 // This file is the replay; it mirrors addTile / addGhostTiles / checkIfNearBoundaries of kestrel_gpu.cu
 // statement for statement on global tile indices.  tests/test_tile_table.py checks it on CPU against the
 // oracle's active and ghost sets, step by step, on the reference's dynamic-tile inputs (world size 2 over
-// gloo: each rank contributes the flags of its own tiles).  Not wired into the library yet.
+// gloo: each rank contributes the flags of its own tiles).  kgpu_dyn_host.inl drives it in decomposed runs.
 #pragma once
 #include <algorithm>
 #include <vector>
@@ -18,7 +18,7 @@
 namespace kgpu {
 
 enum TileOpKind { TOP_LOAD_HEIGHTS = 0, TOP_GHOST_DATA = 1, TOP_ACTIVATE_FRESH = 2, TOP_ACTIVATE_GHOST = 3 };
-struct TileOp { int tile0, kind; };   // 0-based global tile index
+struct TileOp { int tile0, kind, mask; };   // 0-based global tile index; mask: seam bits of a TOP_LOAD_HEIGHTS (tile_vertices_kernel)
 
 struct TileTable {
    int nXt = 0, nYt = 0;
@@ -48,12 +48,22 @@ struct TileTable {
    // GetHeights + the ghost tiles whose seam was refreshed (loadHeights of kestrel_gpu.cu)
    void loadHeights(int t0, bool given) {
       if (loaded[t0] && !given) return;
-      ops.push_back({t0, TOP_LOAD_HEIGHTS});
+      // EqualiseTopographicBoundaryData (MorphodynamicRHS.f90:588-687): a shared vertex keeps the value of the tile for
+      // which it is local index 1, so the east column / north row / north-east corner are only written while the tile
+      // across them has no heights yet
+      int tE = E(t0), tN = oneD ? -1 : N(t0);
+      int tNE = (tE >= 0 && !oneD) ? N(tE) : -1;
+      bool eL = tE >= 0 && tE != t0 && loaded[tE], nL = tN >= 0 && tN != t0 && loaded[tN], neL = tNE >= 0 && loaded[tNE];
+      int mask = 0;
+      if (!eL && !(periodic && nXt == 1)) mask |= 1;
+      if (!nL && !(periodic && nYt == 1)) mask |= 2;
+      if (!(eL || nL || neL) && (mask & 1) && (mask & 2)) mask |= 4;
+      ops.push_back({t0, TOP_LOAD_HEIGHTS, mask});
       loaded[t0] = 1;
       int tW = W(t0), tS = oneD ? -1 : S(t0);
       int tSW = (tW >= 0 && !oneD) ? S(tW) : -1;
       for (int tt : {tW, tS, tSW})
-         if (tt >= 0 && tt != t0 && loaded[tt] && tstate[tt] == 1) ops.push_back({tt, TOP_GHOST_DATA});
+         if (tt >= 0 && tt != t0 && loaded[tt] && tstate[tt] == 1) ops.push_back({tt, TOP_GHOST_DATA, 0});
    }
    // UpdateTiles.f90:389-481
    bool addGhostTiles(int t0) {
@@ -74,7 +84,7 @@ struct TileTable {
          tstate[tt] = 1;
          ghostList.push_back(tt + 1);
          loadHeights(tt, false);
-         ops.push_back({tt, TOP_GHOST_DATA});
+         ops.push_back({tt, TOP_GHOST_DATA, 0});
       }
       return true;
    }
@@ -90,7 +100,7 @@ struct TileTable {
       activeList.insert(std::upper_bound(activeList.begin(), activeList.end(), t0 + 1), t0 + 1);
       if (wasGhost) ghostList.erase(std::find(ghostList.begin(), ghostList.end(), t0 + 1));
       loadHeights(t0, heightsGiven);
-      ops.push_back({t0, wasGhost ? TOP_ACTIVATE_GHOST : TOP_ACTIVATE_FRESH});
+      ops.push_back({t0, wasGhost ? TOP_ACTIVATE_GHOST : TOP_ACTIVATE_FRESH, 0});
       bool ok = addGhostTiles(t0);
       if (countIt) ntilesAdded++;
       return ok;

@@ -35,6 +35,15 @@ struct StatePtrs {
    double *q[4];
 };
 
+// Decomposed runs with dynamic tiles replay the tile operations of the ranks next door on their own halo (tile
+// coordinates -1 or nXt / nYt, kgpu_dyn_host.inl): everything outside the two-cell halo of the storage is dropped.
+__device__ __forceinline__ bool cellInStorage(const DevParams &P, int ci, int cj) {
+   return ci >= -2 && ci < P.NX + 2 && (P.oneD ? cj == 0 : (cj >= -2 && cj < P.NY + 2));
+}
+__device__ __forceinline__ bool vertexInStorage(const DevParams &P, int vi, int vj) {
+   return vi >= -2 && vi <= P.NX + 2 && (P.oneD ? vj == 0 : (vj >= -2 && vj <= P.NY + 2));
+}
+
 // SetDefaultTileData / SetDomainBoundaryData / ActivateTile's "w = b0" (UpdateTiles.f90:342-370, 595-664).
 // kind: 0 = default ghost data into every state buffer, 1 = dirichlet ghost, 2 = activation (w = b0c in S0 only)
 struct AllStates {
@@ -47,6 +56,7 @@ __global__ void tile_default_kernel(const DevParams P, AllStates S, const double
    int lj = blockIdx.y;
    if (li >= P.nX || lj >= P.nY) return;
    int ci = tx * P.nX + li, cj = ty * P.nY + lj;
+   if (!cellInStorage(P, ci, cj)) return;
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    double b0c, btc, bx, by;
    centreTopoGlobal(P, b0v, btv, ci, cj, b0c, btc, bx, by);
@@ -129,6 +139,7 @@ __global__ void import_tile_kernel(const DevParams P, StatePtrs S0, MaximaPtrs M
    int lj = blockIdx.y;
    if (li >= P.nX || lj >= P.nY) return;
    int ci = tx * P.nX + li, cj = ty * P.nY + lj;
+   if (!cellInStorage(P, ci, cj)) return;
    size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
    size_t ncell = (size_t)P.nX * P.nY, k = (size_t)lj * P.nX + li;
    const double *u = stage + k * 13;
@@ -187,6 +198,7 @@ __global__ void tile_vertices_kernel(const DevParams P, double *vfield, double *
    if (dir == 0) { stage[k] = vfield[(size_t)(vj + YO) * P.pitch + (vi + XO)]; return; }
    // periodic: vertex NX aliases vertex 0 (EqualiseTopographicBoundaryData across the wrap)
    if (P.periodic) { if (vi == P.NX) vi = 0; if (!P.oneD && vj == P.NY) vj = 0; }
+   if (!vertexInStorage(P, vi, vj)) return;
    size_t g = (size_t)(vj + YO) * P.pitch + (vi + XO);
    bool right = (li == P.nX), top = (!P.oneD && lj == P.nY);
    if (right && top) { if (!(writeMask & 4)) return; }

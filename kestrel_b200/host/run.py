@@ -33,7 +33,7 @@ def kahan_total(values: np.ndarray) -> float:
 def calculate_volume(rs: RunSet, tiles: Dict[int, dict]):
     """CalculateVolume (Output.f90:617-735) over downloaded active tiles.
     Returns (vol, bed, mass, bed*rhob, solids*rhos, bed*rhos*(1-p))."""
-    dv_all, mass_all, bed_all, sol_all = [], [], [], []
+    dv_all, mass_all, bed_all, sol_all = [np.zeros(0)], [np.zeros(0)], [np.zeros(0)], [np.zeros(0)]
     for tid in sorted(tiles):
         u = tiles[tid]["u"]
         gam = np.sqrt(1.0 + u[..., BX] * u[..., BX] + u[..., BY] * u[..., BY]) if rs.geometric_factors else np.ones_like(u[..., BX])
@@ -76,12 +76,18 @@ def write_solution_txt(rs: RunSet, path: str, tiles: Dict[int, dict]):
 class Simulation:
     """LoadSourceConditions + Run against a library exporting the ABI."""
 
-    def __init__(self, rs: RunSet, lib: capi.Library, device_topography: bool = False):
+    def __init__(self, rs: RunSet, lib: capi.Library, device_topography: bool = False,
+                 after_create: Optional[Callable] = None):
+        """after_create(stepper): called between kgpu_create and the first upload -- a decomposed run attaches its
+        communicator there (kgpu_comm_attach).  Every rank of a decomposed run builds the same initial tiles and
+        uploads all of them (kgpu_upload_tile is collective when tiles are dynamic); downloads cover its own block."""
         self.rs = rs
         self.lib = lib
         self.ic_tiles = load_source_conditions(rs)  # also fills NumCellsInSrc
         p, keep = rs.to_c(make_heights_callback(rs))
         self.stepper = capi.Stepper(lib, p, keep)
+        if after_create:
+            after_create(self.stepper)
         if device_topography:  # tiles activated during the run get their heights from a kernel, not from the callback
             self.stepper.set_topography_function(rs.topog_func, rs.topog_params)
         for tid in sorted(self.ic_tiles):
@@ -96,8 +102,9 @@ class Simulation:
         return {int(t): self.stepper.download_tile(int(t)) for t in self.stepper.active_tiles()}
 
     def initial_tiles(self) -> Dict[int, dict]:
+        own = set(int(t) for t in self.stepper.active_tiles()) if self.rs.comm_size > 1 else None
         return {tid: {"u": T.u.copy(), "b0": T.b0v, "bt": np.zeros_like(T.b0v), "maxima": T.maxima, "tfirst": T.tfirst}
-                for tid, T in self.ic_tiles.items()}
+                for tid, T in self.ic_tiles.items() if own is None or tid in own}
 
     def run(self, out_dir: Optional[str] = None, keep_snapshots: bool = True,
             on_output: Optional[Callable] = None):

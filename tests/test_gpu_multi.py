@@ -52,3 +52,27 @@ def test_decomposed_redistribution_is_bitwise_equal(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout
+
+
+SMALL_TILES_2D = ["--set", "nXpertile=10", "--set", "nYpertile=10", "--set", "Xtilesize=10.0", "--set", "Ytilesize=None", "--set", "Nout=2"]
+DYNAMIC_CASES = [
+    # the reference's inputs with 10-cell tiles, so that the active set grows across the rank seams within tens of steps
+    # (the oracle adds 12 / 12 / 11 tiles on these; tests/run_multigpu_dynamic.py requires growth)
+    ("case_flux_hydro_2d.txt", SMALL_TILES_2D),                          # flux source sitting on the seams
+    ("case_cap_conc_2d.txt", SMALL_TILES_2D + ["--set", "tend=8.0"]),   # released cap with solids
+    ("case_flux_hydro.txt", ["--set", "nXpertile=10", "--set", "Xtilesize=10.0", "--set", "tend=30.0", "--set", "Nout=2"]),   # 1-D
+]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("case,extra", DYNAMIC_CASES)
+def test_decomposed_dynamic_tiles_are_bitwise_equal(world, case, extra):
+    """Non-periodic domain, tiles activated by the flow across rank seams (replicated tile table, kgpu_dyn_host.inl):
+    active and ghost sets, counters, fields, maxima and heights per tile bitwise equal to the 1-GPU run."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29560 + world), os.path.join(ROOT, "tests", "run_multigpu_dynamic.py"), "--case", case] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "PASS" in r.stdout

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2: dynamic tiles across ranks (2 GPUs)
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+W=${W:-2}
+run() {  # name, args...
+   local name=$1; shift
+   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29571 \
+      tests/run_multigpu_dynamic.py "$@" > gpurun_out/r02_dyn_${name}_n$W.log 2>&1
+   echo "== $name rc=$?"; grep -E "MULTIGPU|^    (output|rank|ghost)|Error|KestrelError" gpurun_out/r02_dyn_${name}_n$W.log | head -20
+}
+S2="--set nXpertile=10 --set nYpertile=10 --set Xtilesize=10.0 --set Ytilesize=None --set Nout=2"
+run flux2d --case case_flux_hydro_2d.txt $S2
+run cap2d --case case_cap_conc_2d.txt $S2 --set tend=8.0
+run flux1d --case case_flux_hydro.txt --set nXpertile=10 --set Xtilesize=10.0 --set tend=30.0 --set Nout=2
+run flux2d_fast --case case_flux_hydro_2d.txt $S2 --arithmetic 1
