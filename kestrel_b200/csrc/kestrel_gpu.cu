@@ -24,8 +24,8 @@
 #include "../../include/kestrel_gpu_debug.h"
 #include "kgpu_comm.cuh"
 #include "kgpu_hydro.cuh"
-#include "kgpu_morpho.cuh"
 #include "kgpu_redist_tables.hpp"
+#include "kgpu_morpho.cuh"
 #include "kgpu_tile_table.hpp"
 #include "kgpu_tiles.cuh"
 
@@ -906,11 +906,11 @@ int kgpu_create(const kgpu_params *p, kgpu_handle **out) {
       bool okc = c.px >= 1 && c.py >= 1 && c.px * c.py == c.size && c.rank >= 0 && c.rank < c.size &&
                  p->nXtiles % c.px == 0 && p->nYtiles % c.py == 0 && !(h->oneD && c.py != 1);
       // periodic domains run all-active (kgpu_upload_domain); the others keep dynamic tiles through the replicated
-      // tile table (kgpu_dyn_host.inl) -- hydraulic operator only so far
-      const bool okd = h->globalPeriodic || (!h->morpho && p->nXpertile >= 3 && (h->oneD || p->nYpertile >= 3));
+      // tile table (kgpu_dyn_host.inl)
+      const bool okd = h->globalPeriodic || (p->nXpertile >= 3 && (h->oneD || p->nYpertile >= 3));
       if (!okc || !okd) {
          fprintf(stderr, "kgpu_create: decomposition needs px*py = size and tiles divisible by px, py; without periodic bcs also "
-                         "MorphodynamicsOn = 0 and tiles of at least 3 cells\n");
+                         "tiles of at least 3 cells\n");
          delete h;
          return okc ? KGPU_ERR_UNSUPPORTED : KGPU_ERR_ARG;
       }

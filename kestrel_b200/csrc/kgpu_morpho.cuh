@@ -443,12 +443,16 @@ __global__ void __launch_bounds__(128) morpho_redistribute_wave_kernel(const Dev
 constexpr int RP_V = 16, RP_C = 9;                    // vertices / cells per patch
 constexpr int RP_B0 = 0, RP_BT0 = 16, RP_BT3 = 32;    // vertex fields
 constexpr int RP_W0 = 48, RP_HPSI0 = 57, RP_W3 = 66, RP_HPSI3 = 75;   // cell fields
-constexpr int RP_DOUBLES = 84;
+constexpr int RP_ACT = 84;                                             // 1.0 where the cell's tile is active (dynamic tiles), else 0.0
+constexpr int RP_DOUBLES = 93;
+static_assert(RP_DOUBLES == RT_DOUBLES && RP_W0 == RT_W0 && RP_V == RT_V && RP_C == RT_C, "patch layout of kgpu_redist_tables.hpp");
 
 struct RedistPackArgs {
    const double *b0v, *bt0, *bt3, *w0, *hpsi0, *w3, *hpsi3;
    const RedistEntry *list;   // local entries, local indices
    int n;
+   const uint8_t *tileMask;
+   int allActive;
 };
 // one thread per (entry, patch element)
 __global__ void redist_pack_kernel(const DevParams P, const RedistPackArgs A, double *out) {
@@ -467,6 +471,10 @@ __global__ void redist_pack_kernel(const DevParams P, const RedistPackArgs A, do
       int q = (o - RP_W0) % RP_C; a = q % 3 - 1; b = q / 3 - 1;
    }
    int jj = P.oneD ? 0 : j + b;
+   if (o >= RP_ACT) {   // RedistributeGrid refreshes only cells of active tiles (Redistribute.f90:404-472; the ring of the mask
+      out[k] = cellTileActive(P, A.tileMask, A.allActive, i + a, jj) ? 1.0 : 0.0;   // knows the tiles of the ranks next door)
+      return;
+   }
    out[k] = src[(size_t)(jj + YO) * P.pitch + (i + a + XO)];
 }
 
@@ -489,7 +497,7 @@ __device__ __forceinline__ void centreTopoVals(const DevParams &P, double a, dou
 struct RedistGlobalArgs {
    double *G;            // gathered patches, canonical values live at the slot offsets below
    const int *vslot;     // [n][16] offset of the b0 value of vertex (i-1+a, j-1+b), a + 4 b; bt0 at +16, bt3 at +32
-   const int *cslot;     // [n][9]  offset of the w0 value of cell (i-1+a, j-1+b), a + 3 b; hpsi0 +9, w3 +18, hpsi3 +27
+   const int *cslot;     // [n][9]  offset of the w0 value of cell (i-1+a, j-1+b), a + 3 b; hpsi0 +9, w3 +18, hpsi3 +27, active +36
    int n;
    Ctrl *ctrl;
 };
@@ -554,6 +562,7 @@ __global__ void redist_global_kernel(const DevParams P, const RedistGlobalArgs A
       for (int a = 0; a < 3; a++)
          for (int b = (P.oneD ? 1 : 0); b < (P.oneD ? 2 : 3); b++) {
             const int cc = C(a, b);
+            if (G[cc + 36] == 0.0) continue;   // cell of a ghost or inactive tile: left alone
             double c_b0, c_bt0, c_bx0, c_by0, c_bt3, c_bx3, c_by3;
             centre(a, b, RP_BT0, c_b0, c_bt0, c_bx0, c_by0);
             centre(a, b, RP_BT3, c_b0, c_bt3, c_bx3, c_by3);

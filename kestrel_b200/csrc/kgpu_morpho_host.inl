@@ -70,7 +70,7 @@ static int redistributeAcrossRanks(kgpu_handle *h, int nLocal, int M, int R1, in
       RedistPackArgs pa;
       pa.b0v = h->b0v; pa.bt0 = h->btv[h->bt0]; pa.bt3 = h->btv[h->bt3];
       pa.w0 = h->S[R1][QW]; pa.hpsi0 = h->S[R1][QHPSI]; pa.w3 = h->S[MA][QW]; pa.hpsi3 = h->S[MA][QHPSI];
-      pa.list = h->d_redist; pa.n = nLocal;
+      pa.list = h->d_redist; pa.n = nLocal; pa.tileMask = h->d_tileMask; pa.allActive = h->allActive() ? 1 : 0;
       int nthr = nLocal * RP_DOUBLES;
       redist_pack_kernel<<<(nthr + 255) / 256, 256, 0, h->stream>>>(h->D, pa, B.dSend);
       h->launches++;
@@ -139,7 +139,8 @@ static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
       CUDA_TRY(h, cudaGetLastError());
       return rc;
    }
-   morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
+   // (a rank of a decomposed run may hold no active block: it still takes part in every exchange)
+   if (h->nBlocks > 0) morpho_emd_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
    if (h->comm.active) {   // the bed kernel reads E - D of the cells across the block edge (single device: by wrapped index)
       double *pe[1] = {a.EmD};
       int rce = exchangeHalo(h, pe, 1, false, h->stream);
@@ -150,7 +151,7 @@ static int morphoStageT(kgpu_handle *h, const MorphoArgs &a) {
    double *pl[1] = {a.btn};
    int rc = fillHaloPlanes(h, pl, 1, true);
    if (rc) return rc;
-   morpho_cell_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
+   if (h->nBlocks > 0) morpho_cell_kernel<BX, BY><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, a);
    double *pc[5] = {a.wn, a.hpsin, a.nBx, a.nBy, a.nHn};   // the next stage reads slopes and depths of halo cells
    rc = fillHaloPlanes(h, pc, 5, false);
    h->launches += 3;
@@ -164,12 +165,14 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    const int R1 = h->ib, PRE = h->ia, MA = h->ic, MB = h->id;
    const int allAct = h->allActive() ? 1 : 0;
    int BX = h->oneD ? BX1 : BX2, BY = h->oneD ? BY1 : BY2;
-   if (h->nBlocks == 0) return 0;
+   if (h->nBlocks == 0 && !h->comm.active) return 0;
+   const bool some = h->nBlocks > 0;   // false: a rank without active blocks, which only takes part in the collectives
    // (the halo of the H1 result was produced together with it)
    // velocities frozen over M = those of H1's 4th RHS evaluation (pre-correction momenta)
    // the hydraulic topography planes are those of bt0 here (H1 just ran with them)
    if (h->topoBtIdx != h->bt0 && (rc = computeTopo(h, h->bt0))) return rc;
-   if (h->oneD)
+   if (!some) {}
+   else if (h->oneD)
       morpho_prepare_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, h->S[R1][QW], h->S[R1][QHPSI], h->S[PRE][QHU], h->S[PRE][QHV],
                                                                             h->topo.b0c, h->topo.btc, h->topo.bxc, h->topo.byc, h->Um, h->Vm,
                                                                             h->mcHn0, h->d_tileMask, h->d_blockList, allAct);
@@ -209,7 +212,8 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
    c.w0 = h->S[R1][QW]; c.hpsi0 = h->S[R1][QHPSI]; c.w3 = h->S[MA][QW]; c.b0v = h->b0v; c.bt0 = h->btv[h->bt0]; c.bt3 = h->btv[h->bt3];
    c.b0c = h->topo.b0c; c.zBt = h->topo.btc; c.zGam = h->topo.gamc; c.c3Bt = h->mc[0][0]; c.c3Bx = h->mc[0][1]; c.c3By = h->mc[0][2];
    c.tileMask = h->d_tileMask; c.blockList = h->d_blockList; c.ctrl = h->d_ctrl; c.list = h->d_redist; c.listCap = h->redistCap; c.allActive = allAct;
-   if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
+   if (!some) {}
+   else if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
    h->launches += 2;
    if ((rc = allreduceMorphoFlags(h))) return rc;
@@ -228,7 +232,8 @@ static int strangRemainder(kgpu_handle *h, double t0, double &dt_hydro, bool &ag
          h->nRedistGrows++;
          ctrl_morpho_reset_kernel<<<1, 1, 0, h->stream>>>(h->d_ctrl);
          c.list = h->d_redist; c.listCap = h->redistCap;
-         if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
+         if (!some) {}
+         else if (h->oneD) morpho_check_kernel<BX1, BY1><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
          else morpho_check_kernel<BX2, BY2><<<h->nBlocks, NTHREADS, 0, h->stream>>>(h->D, c);
          h->launches += 2;
          if ((rc = allreduceMorphoFlags(h))) return rc;

@@ -14,7 +14,7 @@
 
 namespace kgpu {
 
-constexpr int RT_V = 16, RT_C = 9, RT_DOUBLES = 84, RT_B0 = 0, RT_W0 = 48;   // patch layout (kgpu_morpho.cuh RP_*)
+constexpr int RT_V = 16, RT_C = 9, RT_DOUBLES = 93, RT_B0 = 0, RT_W0 = 48;   // patch layout (kgpu_morpho.cuh RP_*)
 
 struct RedistTables {
    std::vector<int> patch;          // [n] gathered patch index (r * M + k) of the entries in walk order

@@ -61,6 +61,13 @@ DYNAMIC_CASES = [
     ("case_flux_hydro_2d.txt", SMALL_TILES_2D),                          # flux source sitting on the seams
     ("case_cap_conc_2d.txt", SMALL_TILES_2D + ["--set", "tend=8.0"]),   # released cap with solids
     ("case_flux_hydro.txt", ["--set", "nXpertile=10", "--set", "Xtilesize=10.0", "--set", "tend=30.0", "--set", "Nout=2"]),   # 1-D
+    # morphodynamics (Strang step across ranks with dynamic tiles; RedistributeGrid's replicated walk leaves the cells of
+    # ghost and inactive tiles alone, as the single-device walk does)
+    ("case_cap_morpho_2d.txt", SMALL_TILES_2D + ["--set", "tend=2.0"]),                  # ~4600 redistributed cells, active set across the seam
+    ("case_tile_indep_dynamic_20m.txt", ["--set", "tend=2.0", "--set", "Nout=2"]),       # world 2: one rank holds ghost tiles only
+    ("case_flux_morpho_2d.txt", SMALL_TILES_2D + ["--set", "tend=5.0"]),
+    ("case_cap_morpho.txt", ["--set", "nXpertile=20", "--set", "Xtilesize=20.0", "--set", "tend=5.0", "--set", "Nout=2"]),   # 1-D
+    ("case_flux_morpho.txt", ["--set", "nXpertile=10", "--set", "Xtilesize=10.0", "--set", "tend=10.0", "--set", "Nout=2"]),  # 1-D, 2600 refinements
 ]
 
 
@@ -68,7 +75,7 @@ DYNAMIC_CASES = [
 @pytest.mark.parametrize("case,extra", DYNAMIC_CASES)
 def test_decomposed_dynamic_tiles_are_bitwise_equal(world, case, extra):
     """Non-periodic domain, tiles activated by the flow across rank seams (replicated tile table, kgpu_dyn_host.inl):
-    active and ghost sets, counters, fields, maxima and heights per tile bitwise equal to the 1-GPU run."""
+    active and ghost sets, counters, fields, bed, maxima and heights per tile bitwise equal to the 1-GPU run."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",

@@ -76,7 +76,7 @@ def test_walk_order_and_canonical_slots(px, py):
             for q in range(n_per):
                 k = ((gi[e] - 1 + q % width) % NXg, (gj[e] - 1 + q // width) % NYg)
                 s = int(slots[e, q])
-                p2, off = divmod(s, 84)
+                p2, off = divmod(s, 93)
                 q2 = off - first
                 assert 0 <= q2 < n_per
                 e2 = int(np.nonzero(patch == p2)[0][0])
@@ -97,7 +97,7 @@ def test_one_dimensional_patches():
     gi = li[patch] + (patch // M) * NX
     for e in range(len(patch)):
         for q in range(16):   # every row of a 1-D patch is row 0
-            p2, off = divmod(int(vslot[e, q]), 84)
+            p2, off = divmod(int(vslot[e, q]), 93)
             e2 = int(np.nonzero(patch == p2)[0][0])
             assert (gi[e2] - 1 + off % 4) % 128 == (gi[e] - 1 + q % 4) % 128
 

@@ -11,7 +11,16 @@ run() {  # name, args...
    echo "== $name rc=$?"; grep -E "MULTIGPU|^    (output|rank|ghost)|Error|KestrelError" gpurun_out/r02_dyn_${name}_n$W.log | head -20
 }
 S2="--set nXpertile=10 --set nYpertile=10 --set Xtilesize=10.0 --set Ytilesize=None --set Nout=2"
+if [ "${HYDRO:-1}" = 1 ]; then
 run flux2d --case case_flux_hydro_2d.txt $S2
 run cap2d --case case_cap_conc_2d.txt $S2 --set tend=8.0
 run flux1d --case case_flux_hydro.txt --set nXpertile=10 --set Xtilesize=10.0 --set tend=30.0 --set Nout=2
 run flux2d_fast --case case_flux_hydro_2d.txt $S2 --arithmetic 1
+fi
+# morphodynamics: redistribution with dynamic tiles across the seam, a rank without active tiles, 1-D
+run capm2d --case case_cap_morpho_2d.txt $S2 --set tend=2.0
+run indep20 --case case_tile_indep_dynamic_20m.txt --set tend=2.0 --set Nout=2
+run fluxm2d --case case_flux_morpho_2d.txt $S2 --set tend=5.0
+run capm1d --case case_cap_morpho.txt --set nXpertile=20 --set Xtilesize=20.0 --set tend=5.0 --set Nout=2
+run fluxm1d --case case_flux_morpho.txt --set nXpertile=10 --set Xtilesize=10.0 --set tend=10.0 --set Nout=2
+run capm2d_fast --case case_cap_morpho_2d.txt $S2 --set tend=2.0 --arithmetic 1
