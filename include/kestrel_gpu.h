@@ -185,9 +185,9 @@ int kgpu_integrate_to(kgpu_handle *h, double tend, int64_t max_steps, kgpu_step_
  * ids may be NULL to query n only.
  * Tile ids everywhere in this interface (upload, download, the two lists, the heights
  * callback) number the WHOLE tile grid, 1-based with tx fastest, as the reference's
- * tileContainer index does.  A decomposed handle (comm_size > 1) lists, accepts and
- * requests only the tiles of its own block (kgpu_comm_block) and answers
- * KGPU_ERR_ARG for another rank's tile. */
+ * tileContainer index does.  A decomposed handle (comm_size > 1) lists and downloads
+ * only the tiles of its own block (kgpu_comm_block) and answers KGPU_ERR_ARG for
+ * another rank's tile; see kgpu_comm_attach for uploads. */
 int kgpu_active_tiles(kgpu_handle *h, int32_t *n, int32_t *ids);
 int kgpu_ghost_tiles(kgpu_handle *h, int32_t *n, int32_t *ids);
 
@@ -284,7 +284,19 @@ int kgpu_comm_create_id(void *id_out);
  * interior of the stage kernel, and one ncclAllReduce(min) per dt decision keeps every rank
  * on the same time step.  The morphodynamic operator exchanges E - D, the stage beds and its
  * centre planes the same way, max-reduces its refine flags, and replays RedistributeGrid
- * identically on every rank over all-gathered patches.  Periodic, all tiles active. */
+ * identically on every rank over all-gathered patches.
+ * Two modes, chosen by the boundary conditions:
+ *  - periodic: every tile active, state moved in bulk with kgpu_upload_domain /
+ *    kgpu_download_domain (kgpu_upload_tile takes the rank's own tiles);
+ *  - halt / dirichlet: dynamic tiles as on one device (src/UpdateTiles.f90,
+ *    CheckIfNearBoundaries src/TimeStepper.f90:924-1150): the tile table is replicated, so
+ *    kgpu_upload_tile is COLLECTIVE -- every rank passes every initial tile with the same
+ *    arguments in the same order -- and the heights callback may be asked for tiles of the
+ *    neighbouring ranks that reach into this rank's halo.  kgpu_active_tiles,
+ *    kgpu_ghost_tiles and kgpu_download_tile cover the rank's own block; step counters and
+ *    tiles added are those of the whole domain.  Tiles need at least 3 cells a side.
+ *    kgpu_load_source_conditions is single-device only.
+ * In both modes the decomposed run is bit-identical to the single-device run. */
 int kgpu_comm_attach(kgpu_handle *h, const void *id);
 /* Tile block owned by this handle (0-based global tile coordinates). */
 int kgpu_comm_block(kgpu_handle *h, int32_t *tx0, int32_t *ty0, int32_t *ntx, int32_t *nty);
