@@ -323,6 +323,7 @@ static int refreshMasks(kgpu_handle *h) {
 // cells around the active region are static ghost data.
 static int exchangeHalo(kgpu_handle *h, double *const *planes, int nf, bool vertices, cudaStream_t s);
 static int allreduceCfl(kgpu_handle *h, int slot);
+static int allreduceNonfinite(kgpu_handle *h);
 
 static int fillHaloCells(kgpu_handle *h, int k) {
    if (h->comm.active) return exchangeHalo(h, h->S[k], 4, false, h->stream);
@@ -750,6 +751,7 @@ static int hydraulicTimeStepper(kgpu_handle *h, int kq0, int ka, int kb, int kbt
    // stamp: every test there is a strict `>` (or tfirst == -1) against values the first pass has just stored, so that
    // pass cannot change anything and is not launched (round 1 ran a maxima_kernel here: 2 % of the Strang step).
    CUDA_TRY(h, cudaGetLastError());
+   if ((rc = allreduceNonfinite(h))) return rc;
    return readCtrl(h);
 }
 

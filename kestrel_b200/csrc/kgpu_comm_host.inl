@@ -3,7 +3,18 @@
 // libnccl is resolved at run time (dlopen of the soname already loaded by the host process,
 // e.g. the one torch ships) so that single-GPU users need no NCCL at all.
 #include <dlfcn.h>
+#if __has_include(<nccl.h>) && !defined(KGPU_NO_NCCL_HEADER)
 #include <nccl.h>
+#else
+// No NCCL headers on the build machine: the handful of declarations the plumbing needs, with the values of NCCL 2.x's
+// public ABI (nccl.h: ncclResult_t, ncclDataType_t, ncclRedOp_t, NCCL_UNIQUE_ID_BYTES).  The library itself is still
+// only resolved at run time.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclChar = 0, ncclInt = 2, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+#endif
 
 struct NcclApi {
    void *lib = nullptr;
@@ -123,6 +134,14 @@ static int allreduceCfl(kgpu_handle *h, int slot) {
    if (!h->comm.active) return 0;
    double *p = reinterpret_cast<double *>(&h->d_ctrl->cflBits[slot]);
    NCCL_TRY(h, g_nccl.AllReduce(p, p, 1, ncclDouble, ncclMin, (ncclComm_t)h->comm.nccl, h->stream));
+   return 0;
+}
+
+// A state that went non-finite on one rank must stop every rank (a rank returning alone would leave the others
+// waiting in the next exchange): the flag is max-reduced before the host reads the control block.
+static int allreduceNonfinite(kgpu_handle *h) {
+   if (!h->comm.active) return 0;
+   NCCL_TRY(h, g_nccl.AllReduce(&h->d_ctrl->nonfinite, &h->d_ctrl->nonfinite, 1, ncclInt, ncclMax, (ncclComm_t)h->comm.nccl, h->stream));
    return 0;
 }
 

@@ -56,6 +56,9 @@ def main():
     ap.add_argument("--set", action="append", help="RunSet attribute override, e.g. --set Nout=2 --set DeltaT=1.5")
     ap.add_argument("--arithmetic", type=int, default=0)
     ap.add_argument("--px", type=int, default=0)
+    ap.add_argument("--expect-halt", action="store_true",
+                    help="the flow reaches the domain edge under Boundary Conditions = halt: every rank and the single device must stop "
+                         "with KGPU_ERR_HALT_BC (UpdateTiles.f90:63-65) after the same number of steps")
     args = ap.parse_args()
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lrank)
@@ -72,6 +75,31 @@ def main():
     rs.comm_rank, rs.comm_size, rs.comm_px, rs.comm_py = rank, world, px, py
     rs.finalize()
     sim = Simulation(rs, lib, after_create=lambda st: attach(lib, st, rank, dev))
+    if args.expect_halt:
+        def until_error(s):
+            try:
+                s.run()
+            except capi.KestrelError as e:
+                return (e.code, [(i.t, i.nsteps, i.nrefines, i.ntiles_added) for i in s.infos], sorted(int(t) for t in s.stepper.active_tiles()))
+            return (0, [], [])
+        mine = until_error(sim)
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, 0)
+        ok = True
+        if rank == 0:
+            rs1 = make_runset(args)
+            rs1.device = lrank
+            rs1.finalize()
+            ref = until_error(Simulation(rs1, lib))
+            union = sorted(t for r in range(world) for t in parts[r][2])
+            ok = ref[0] == 3 and all(p[0] == 3 and p[1] == ref[1] for p in parts) and union == ref[2]
+            print(f"MULTIGPU-DYNAMIC world={world} decomposition={px}x{py} case={args.case} expect-halt: codes={[p[0] for p in parts]} "
+                  f"reference={ref[0]} completed outputs={len(ref[1])} active tiles at the stop={len(ref[2])} -> {'PASS' if ok else 'FAIL'}", flush=True)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.broadcast(flag, 0)
+        sim.stepper.close()
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag.item()) == 1 else 1)
     sim.run()
     mine = pack(sim)
     parts = [None] * world if rank == 0 else None

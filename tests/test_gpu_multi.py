@@ -68,6 +68,12 @@ DYNAMIC_CASES = [
     ("case_flux_morpho_2d.txt", SMALL_TILES_2D + ["--set", "tend=5.0"]),
     ("case_cap_morpho.txt", ["--set", "nXpertile=20", "--set", "Xtilesize=20.0", "--set", "tend=5.0", "--set", "Nout=2"]),   # 1-D
     ("case_flux_morpho.txt", ["--set", "nXpertile=10", "--set", "Xtilesize=10.0", "--set", "tend=10.0", "--set", "Nout=2"]),  # 1-D, 2600 refinements
+    # an 8 x 8 tile grid the flux source fills within 20 s: dirichlet edges (ghost tiles on the domain edge carry the
+    # boundary state, inflow included; 35 of the 36 interior tiles end up active) ...
+    ("case_flux_hydro_2d.txt", SMALL_TILES_2D + ["--set", "nXtiles=8", "--set", "nYtiles=8", "--set", "tend=20.0", "--set", "bcs=dirichlet",
+                                                 "--set", "bcsHnval=0.02", "--set", "bcsuval=0.1"]),
+    # ... and halt edges: every rank stops with KGPU_ERR_HALT_BC at the same step as one device does
+    ("case_flux_hydro_2d.txt", SMALL_TILES_2D + ["--set", "nXtiles=8", "--set", "nYtiles=8", "--set", "tend=20.0", "--expect-halt"]),
 ]
 
 

@@ -24,3 +24,8 @@ run fluxm2d --case case_flux_morpho_2d.txt $S2 --set tend=5.0
 run capm1d --case case_cap_morpho.txt --set nXpertile=20 --set Xtilesize=20.0 --set tend=5.0 --set Nout=2
 run fluxm1d --case case_flux_morpho.txt --set nXpertile=10 --set Xtilesize=10.0 --set tend=10.0 --set Nout=2
 run capm2d_fast --case case_cap_morpho_2d.txt $S2 --set tend=2.0 --arithmetic 1
+S8="$S2 --set nXtiles=8 --set nYtiles=8 --set tend=20.0"
+run dirichlet --case case_flux_hydro_2d.txt $S8 --set bcs=dirichlet --set bcsHnval=0.02 --set bcsuval=0.1
+run halt --case case_flux_hydro_2d.txt $S8 --expect-halt
+# the periodic all-active path after the non-finite allreduce
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$W --master-addr 127.0.0.1 --master-port 29572 tests/run_multigpu.py --tiles 8 --per 32 --steps 25 2>&1 | grep MULTIGPU
