@@ -105,29 +105,7 @@ __global__ void tile_flags_kernel(const DevParams P, StatePtrs S0, const double 
    if (threadIdx.x == 0) flagsOut[blockIdx.x] = s_flags;
 }
 
-// Running maxima (TimeStepper.f90:1155-1303), evaluated on the state at the START of the
-// step and stamped with its END time (quirk Q1, TimeStepper.f90:519-524).
-template <int BX, int BY>
-__global__ void __launch_bounds__(256) maxima_kernel(const DevParams P, StatePtrs S0, const double *b0v, const double *btv,
-                                                        MaximaPtrs M, const uint8_t *tileMask, const int2 *blockList,
-                                                        const Ctrl *ctrl, int allActive) {
-   if (ctrl->failed) return;
-   if (threadIdx.x >= BX * BY) return;
-   const int2 bo = blockList[blockIdx.x];
-   int ci = bo.x * BX + threadIdx.x % BX, cj = bo.y * BY + threadIdx.x / BX;
-   if (ci >= P.NX || cj >= P.NY) return;
-   if (!allActive) {
-      int tx = ci / P.nX + 1, ty = cj / P.nY + 1;
-      if (tileMask[ty * (P.nXt + 2) + tx] != 2) return;
-   }
-   size_t g = (size_t)(cj + YO) * P.pitch + (ci + XO);
-   double tt = ctrl->t + ctrl->dt;  // nextT
-   CellState q;
-   q.w = S0.q[QW][g]; q.hu = S0.q[QHU][g]; q.hv = S0.q[QHV][g]; q.hpsi = S0.q[QHPSI][g];
-   centreTopoGlobal(P, b0v, btv, ci, cj, q.b0, q.bt, q.bx, q.by);
-   desingularise(P, q, true);
-   updateMaxima(P, M, g, tt, q.Hn, sqrt(speed2(P, q.u, q.v, q.bx, q.by)), q.bt, q.psi);
-}
+// (Running maxima, TimeStepper.f90:1155-1303: updateMaxima in kgpu_device.cuh, called from the final stage of K1.)
 
 // ---- host transfer staging: one tile <-> one contiguous staging buffer
 // staging layout: [u13 (13,nX,nY)] [maxima 5*(nX,nY,2)] [tfirst (nX,nY)] [b0v (nX+1,nY+1)] [btv (nX+1,nY+1)]
