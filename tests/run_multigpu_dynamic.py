@@ -59,7 +59,16 @@ def main():
     ap.add_argument("--expect-halt", action="store_true",
                     help="the flow reaches the domain edge under Boundary Conditions = halt: every rank and the single device must stop "
                          "with KGPU_ERR_HALT_BC (UpdateTiles.f90:63-65) after the same number of steps")
+    ap.add_argument("--dry-run", action="store_true", help="parse the arguments, build the run settings and the initial tiles on the host, exit")
     args = ap.parse_args()
+    if args.dry_run:   # CPU check of the command lines tests/test_gpu_multi.py builds (tests/test_decomp_gloo.py)
+        from kestrel_b200.host.sources import load_source_conditions
+        rs = make_runset(args)
+        rs.finalize()
+        tiles = load_source_conditions(rs)
+        print(f"DRY-RUN case={args.case} tiles={rs.nXtiles}x{rs.nYtiles} of {rs.nXpertile}x{rs.nYpertile} bcs={rs.bcs} tend={rs.tend} "
+              f"Nout={rs.Nout} morpho={rs.MorphodynamicsOn} initial tiles={sorted(tiles)}")
+        return
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lrank)
     dev = torch.device("cuda", lrank)

@@ -103,3 +103,24 @@ def test_block_ownership_rule():
                     assert (tx, ty) not in seen
                     seen.add((tx, ty))
         assert len(seen) == rs.nXtiles * rs.nYtiles
+
+
+def test_dynamic_multigpu_command_lines_parse():
+    """The command lines tests/test_gpu_multi.py builds for the dynamic-tile runs (reference inputs with overridden tile
+    sizes, boundary conditions and end times) are parsed by the runner on CPU: run settings, decomposability of the tile
+    grid over 2 x 1 / 2 x 2 / 4 x 1 ranks, and initial tiles that the host rasteriser actually produces."""
+    import re
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_multi as tgm
+    for case, extra in tgm.DYNAMIC_CASES:
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "run_multigpu_dynamic.py"), "--case", case, "--dry-run"] + list(extra)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+        m = re.search(r"DRY-RUN case=\S+ tiles=(\d+)x(\d+) of (\d+)x(\d+) bcs=(\w+) .* initial tiles=\[(.*)\]", r.stdout)
+        assert m, r.stdout
+        ntx, nty, nx, ny = (int(m.group(k)) for k in range(1, 5))
+        assert ntx % 4 == 0 or (ntx % 2 == 0 and (nty == 1 or nty % 2 == 0)), (case, ntx, nty)
+        assert nx >= 3 and (nty == 1 or ny >= 3)
+        assert m.group(5) in ("halt", "dirichlet")
+        assert len(m.group(6).split(",")) >= 2
