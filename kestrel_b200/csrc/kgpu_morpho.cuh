@@ -17,7 +17,12 @@ struct RedistEntry {
    int i, j;
 };
 
-__device__ __forceinline__ int wrapIdx(int i, int n, int periodic) { return periodic ? ((i % n) + n) % n : i; }
+// periodic image of an index.  Nearly every call is already in range: the two run-time modulos (≈ 40 instructions, and four
+// such indices per vertex made morpho_bed_kernel issue-bound: 81 % of the issue slots busy at 2 TB/s) are only paid at the wrap
+__device__ __forceinline__ int wrapIdx(int i, int n, int periodic) {
+   if (!periodic || (unsigned)i < (unsigned)n) return i;
+   return ((i % n) + n) % n;
+}
 
 struct MorphoArgs {
    const double *w, *hpsi;      // stage state (w, Hnpsi)
@@ -128,7 +133,7 @@ __global__ void morpho_bed_kernel(const DevParams P, const MorphoArgs A) {
    double rhs;
    auto emd = [&](int i, int j) -> double {
       if (!wrapOrHalo && (i < 0 || i >= P.NX || j < 0 || j >= P.NY)) return 0.0;
-      if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
+      i = wrapIdx(i, P.NX, P.periodic); j = wrapIdx(j, P.NY, P.periodic);
       return A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
    };
    // centre slopes of a cell next to the vertex: the stage's plane inside active tiles (halo images
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(256, 4) morpho_stage_kernel(const DevParams P,
       if (EMDPLANE) {   // morpho_bed_kernel's read of the plane: wrapped index on a periodic device, zero outside the domain
          if (inDomain || image) {
             int i = ci, j = cj;
-            if (P.periodic) { i = ((i % P.NX) + P.NX) % P.NX; j = ((j % P.NY) + P.NY) % P.NY; }
+            i = wrapIdx(i, P.NX, P.periodic); j = wrapIdx(j, P.NY, P.periodic);
             val = A.EmD[(size_t)(j + YO) * P.pitch + (i + XO)];
          }
       } else if ((inDomain || image) && cellTileActive(P, A.tileMask, A.allActive, ci, cj)) {
